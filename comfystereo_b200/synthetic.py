@@ -1,0 +1,79 @@
+"""Seeded synthetic image + depth frames shared by tests, bench.py and
+the golden-fixture generator.  numpy PCG64 streams only, so every machine sees the same bytes.
+
+Depth classes exercise different failure modes of the warp:
+  'scene'   smooth ramp + 3 discs + 1% noise (the benchmark input)
+  'noise'   white noise (worst-case occlusion)
+  'quant'   the scene quantised to a few 8-bit levels (exact closeness ties, Q7)
+  'flat'    constant depth (max == min -> zeros)
+  'steps'   vertical bars at a handful of levels (hard edges for the blur)
+  'card'    the reference's own create_test_images.py layout (3 discs on a vertical ramp)
+"""
+import numpy as np
+
+
+def make_image(n, h, w, seed=0, black_box=False):
+    rng = np.random.default_rng(1000 + seed)
+    img = rng.random((n, h, w, 3), dtype=np.float32)
+    if black_box:  # genuinely black source pixels (mask quirk Q6)
+        img[:, h // 4:h // 2, w // 4:w // 2, :] = 0.0
+    return img
+
+
+def _discs(h, w, shift=0.0):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    d = 0.25 + 0.2 * xx / w + 0.1 * yy / h
+    for cx, cy, r, v in ((0.30, 0.35, 0.15, 0.6), (0.65, 0.55, 0.20, 0.8), (0.50, 0.80, 0.08, 1.0)):
+        m = (xx - (cx + shift) * w) ** 2 + (yy - cy * h) ** 2 <= (r * h) ** 2
+        d = np.where(m, np.float32(v), d)
+    return d.astype(np.float32)
+
+
+def make_depth(n, h, w, kind="scene", seed=0, channels=3, scale255=False):
+    rng = np.random.default_rng(2000 + seed)
+    out = np.empty((n, h, w), np.float32)
+    for i in range(n):
+        shift = 0.002 * i  # discs drift frame to frame (video)
+        if kind == "scene":
+            d = _discs(h, w, shift) + 0.01 * rng.random((h, w), dtype=np.float32)
+        elif kind == "noise":
+            d = rng.random((h, w), dtype=np.float32)
+        elif kind == "quant":
+            d = np.round(_discs(h, w, shift) * 12.0) / 12.0
+            d = np.round(d * 255.0) / 255.0
+        elif kind == "flat":
+            d = np.full((h, w), 0.5, np.float32)
+        elif kind == "steps":
+            levels = np.array([0.1, 0.9, 0.3, 0.7, 0.2, 1.0, 0.0, 0.5], np.float32)
+            d = np.broadcast_to(levels[(np.arange(w) * 8 // max(w, 1)) % 8], (h, w)).copy()
+            d[h // 3: 2 * h // 3, w // 5: 3 * w // 5] = 0.95
+        elif kind == "card":
+            yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+            d = (80.0 + 50.0 * yy / h) / 255.0
+            for cx, cy, r, v in ((0.25, 0.5, 0.166, 100), (0.5, 0.5, 0.2, 170), (0.75, 0.5, 0.133, 240)):
+                d = np.where((xx - cx * w) ** 2 + (yy - cy * h) ** 2 <= (r * h) ** 2, np.float32(v / 255.0), d)
+            d = np.floor(d * 255.0) / 255.0
+        else:
+            raise ValueError(kind)
+        out[i] = np.clip(d, 0.0, 1.0)
+    if scale255:
+        out = out * np.float32(255.0)
+    if channels == 1:
+        return out[..., None].copy()
+    return np.repeat(out[..., None], 3, axis=-1)
+
+
+def index_probe_image(h, w):
+    """uint8-exact image encoding (column + 1) in R,G and a constant in B:
+    after any uint8 CPU fill, R + 256*G - 1 is the source column, 0 means 'unfilled'."""
+    col = np.arange(w, dtype=np.int64) + 1
+    img = np.zeros((h, w, 3), np.uint8)
+    img[..., 0] = (col & 255)[None, :]
+    img[..., 1] = (col >> 8)[None, :]
+    img[..., 2] = 77
+    return img
+
+
+def probe_to_float(img_u8):
+    """float image whose truncating quantisation (Q2) gives back img_u8 exactly."""
+    return ((img_u8.astype(np.float32) + np.float32(0.5)) / np.float32(255.0)).astype(np.float32)

@@ -1,0 +1,227 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference does not exist on the
+GPU box):      python oracle/make_golden.py
+
+Two fixture families, both small enough for git (inputs are regenerated from seeds by
+comfystereo_b200/synthetic.py and guarded by a CRC stored in the fixture):
+
+  node_*.npz   StereoImageNode.generate(...) end to end (GS:79-353): the 4 returned tensors.
+               CPU techniques are stored as uint8 (the node returns uint8/255 exactly),
+               'GPU Warp (Fast)' as float32.
+  stage_*.npz  single hot-path functions called directly on explicit inputs:
+               directional_motion_blur_gpu (SIG:1171), apply_stereo_divergence_* (SIG:1715-1992)
+               on an index-probe image (exact source-column view), forward_warp_gpu (SIG:277).
+"""
+import json
+import os
+import sys
+import warnings
+import zlib
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+from comfystereo_b200 import synthetic as syn  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+DEFAULTS = dict(divergence=4.5, separation=0.0, modes="left-right", stereo_balance=0.0,
+                convergence_point=0.5, stereo_offset_exponent=2.0, fill_technique="GPU Warp (Fast)",
+                depth_blur_edge_threshold=20.0, depth_blur_strength=20.0, depth_map_blur=True,
+                depth_blur_falloff=2.0, depth_blur_vert_smooth=6, batch_size=12)
+
+CPU_FILLS = ['No fill', 'No fill - Reverse projection', 'Imperfect fill - Hybrid Edge', 'Fill - Naive',
+             'Fill - Naive interpolating', 'Fill - Polylines Soft', 'Fill - Polylines Sharp']
+
+
+def node_cases():
+    cases = []
+
+    def add(name, n, h, w, kind, **kw):
+        spec = dict(name=name, n=n, h=h, w=w, kind=kind, seed=len(cases), channels=3,
+                    scale255=False, black_box=False)
+        for k in ("channels", "scale255", "black_box"):
+            if k in kw:
+                spec[k] = kw.pop(k)
+        p = dict(DEFAULTS)
+        p.update(kw)
+        spec["params"] = p
+        cases.append(spec)
+
+    # every dropdown technique on the benchmark-like scene, big shifts for a small frame
+    for i, fill in enumerate(CPU_FILLS + ['GPU Warp (Fast)']):
+        add(f"scene_{i}", 2, 40, 96, "scene", fill_technique=fill, divergence=12.0)
+    # BASELINE.json configs at fixture size
+    add("cfg1_naive", 1, 48, 48, "scene", fill_technique='Fill - Naive', divergence=3.5, depth_map_blur=False)
+    add("cfg2_polysharp", 1, 36, 128, "scene", fill_technique='Fill - Polylines Sharp', divergence=3.5)
+    add("cfg3_hybrid", 3, 36, 96, "scene", fill_technique='Imperfect fill - Hybrid Edge', divergence=3.5)
+    add("cfg4_gpuwarp_anaglyph", 3, 32, 96, "scene", fill_technique='GPU Warp (Fast)',
+        modes='red-cyan-anaglyph', divergence=10.0, batch_size=2)
+    add("cfg5_poly_balance", 1, 32, 128, "scene", fill_technique='Fill - Polylines Sharp',
+        stereo_balance=0.5, divergence=4.5)
+    # modes
+    for i, mode in enumerate(["right-left", "top-bottom", "bottom-top", "red-cyan-anaglyph"]):
+        add(f"mode_{i}", 1, 24, 64, "scene", fill_technique='Fill - Polylines Soft', modes=mode, divergence=8.0)
+        add(f"mode_gw_{i}", 2, 24, 64, "scene", fill_technique='GPU Warp (Fast)', modes=mode, divergence=8.0)
+    # depth classes x techniques
+    for kind in ("noise", "quant", "flat", "steps", "card"):
+        for fill in ('Fill - Polylines Sharp', 'Fill - Naive', 'Imperfect fill - Hybrid Edge',
+                     'No fill - Reverse projection', 'GPU Warp (Fast)', 'Fill - Naive interpolating'):
+            short = fill.split(' - ')[-1].replace(' ', '').replace('(Fast)', '')
+            add(f"{kind}_{short}", 1, 32, 80, kind, fill_technique=fill, divergence=10.0)
+    # parameter corners
+    add("conv0", 1, 32, 80, "scene", fill_technique='Fill - Polylines Sharp', convergence_point=0.0, divergence=9.0)
+    add("conv1", 1, 32, 80, "scene", fill_technique='Fill - Polylines Soft', convergence_point=1.0, divergence=9.0)
+    add("sep_pos", 1, 32, 80, "scene", fill_technique='Fill - Naive', separation=2.5, divergence=9.0)
+    add("sep_neg", 1, 32, 80, "scene", fill_technique='Fill - Polylines Sharp', separation=-3.0, divergence=9.0)
+    add("bal_hi", 1, 32, 80, "scene", fill_technique='Fill - Polylines Sharp', stereo_balance=0.95, divergence=0.05)
+    add("bal_lo_gw", 2, 32, 80, "scene", fill_technique='GPU Warp (Fast)', stereo_balance=-0.95, divergence=0.05)
+    add("exp1", 1, 32, 80, "scene", fill_technique='Fill - Polylines Sharp', stereo_offset_exponent=1.0, divergence=6.0)
+    add("exp07", 1, 32, 80, "scene", fill_technique='No fill', stereo_offset_exponent=0.7, divergence=6.0)
+    add("exp13_gw", 1, 32, 80, "scene", fill_technique='GPU Warp (Fast)', stereo_offset_exponent=1.3, divergence=6.0)
+    add("depth255", 1, 32, 80, "scene", fill_technique='Fill - Naive', scale255=True, divergence=9.0)
+    add("depth255_gw", 2, 32, 80, "scene", fill_technique='GPU Warp (Fast)', scale255=True, divergence=9.0)
+    add("depth1ch", 1, 32, 80, "scene", fill_technique='Fill - Polylines Soft', channels=1, divergence=9.0)
+    add("blackbox", 1, 32, 80, "scene", fill_technique='Fill - Naive', black_box=True, divergence=9.0)
+    add("blur_odd", 1, 32, 80, "steps", fill_technique='Fill - Polylines Sharp', depth_blur_strength=7.3,
+        depth_blur_edge_threshold=4.0, depth_blur_falloff=1.0, depth_blur_vert_smooth=0, divergence=9.0)
+    add("blur_wide", 1, 40, 96, "steps", fill_technique='No fill', depth_blur_strength=33.5,
+        depth_blur_edge_threshold=2.0, depth_blur_falloff=0.5, depth_blur_vert_smooth=15, divergence=9.0)
+    add("blur_off_gw", 2, 32, 80, "scene", fill_technique='GPU Warp (Fast)', depth_map_blur=False, divergence=9.0)
+    add("batch_tail", 5, 24, 64, "scene", fill_technique='Fill - Naive', batch_size=2, divergence=9.0)
+    add("batch_tail_gw", 5, 24, 64, "scene", fill_technique='GPU Warp (Fast)', batch_size=2, divergence=9.0)
+    return cases
+
+
+def crc(*arrays):
+    c = 0
+    for a in arrays:
+        c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    return c
+
+
+def case_inputs(spec):
+    img = syn.make_image(spec["n"], spec["h"], spec["w"], seed=spec["seed"], black_box=spec["black_box"])
+    dep = syn.make_depth(spec["n"], spec["h"], spec["w"], spec["kind"], seed=spec["seed"],
+                         channels=spec["channels"], scale255=spec["scale255"])
+    return img, dep
+
+
+def run_node(spec):
+    """Runs the real node.  The reference's blur function is wrapped (not altered) so that the
+    float32 blurred depth it produced is captured alongside the outputs: torch's conv2d
+    summation order cannot be restated, so downstream integer parity is checked stage-wise by
+    feeding THIS blurred depth to the implementation under test (parity protocol)."""
+    Node = ref_loader.load_node_class()
+    sig = sys.modules[Node.__module__].sig
+    img, dep = case_inputs(spec)
+    captured = []
+    real_blur = sig.directional_motion_blur_gpu
+
+    def spy(depth_tensor, *a, **k):
+        L, R = real_blur(depth_tensor, *a, **k)
+        captured.append((L.detach().cpu().numpy().copy(), R.detach().cpu().numpy().copy()))
+        return L, R
+
+    sig.directional_motion_blur_gpu = spy
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = Node().generate(torch.from_numpy(img), torch.from_numpy(dep), **spec["params"])
+    finally:
+        sig.directional_motion_blur_gpu = real_blur
+    blur = None
+    if captured:
+        L = np.concatenate([c[0].reshape(-1, spec["h"], spec["w"]) for c in captured])
+        R = np.concatenate([c[1].reshape(-1, spec["h"], spec["w"]) for c in captured])
+        blur = (L.astype(np.float32), R.astype(np.float32))
+    return img, dep, [o.numpy() for o in out], blur
+
+
+def stage_cases():
+    cases = []
+    for kind in ("scene", "noise", "quant", "steps", "card"):
+        for (s, thr, fo, v) in ((20, 20, 2.0, 6), (5.5, 3, 1.0, 0), (33.3, 1.0, 1.5, 15), (2.5, 20, 3.0, 1)):
+            cases.append(dict(stage="blur", kind=kind, h=40, w=112, seed=len(cases),
+                              strength=s, thr=thr, falloff=fo, vert=v))
+    fills = ["none", "naive", "naive_interpolating", "polylines_soft", "polylines_sharp", "inverse", "hybrid_edge"]
+    for kind in ("scene", "noise", "quant", "steps", "flat"):
+        for (div, sep, expo, conv) in ((12.0, 0.0, 2.0, 0.5), (-9.0, 1.5, 1.0, 0.0), (7.0, -2.0, 0.7, 1.0)):
+            for fill in fills:
+                cases.append(dict(stage="warp", kind=kind, h=24, w=300, seed=len(cases), fill=fill,
+                                  div=div, sep=sep, expo=expo, conv=conv))
+    for kind in ("scene", "noise", "quant", "steps"):
+        for (div, sep, expo, conv) in ((25.0, 0.0, 2.0, 0.5), (-18.0, 2.0, 1.0, 0.2), (11.0, -1.0, 0.5, 0.8)):
+            cases.append(dict(stage="gpuwarp", kind=kind, h=24, w=160, seed=len(cases),
+                              div_px=div, sep_px=sep, expo=expo, conv=conv))
+    return cases
+
+
+def run_stage(spec):
+    sig = ref_loader.load_sig()
+    h, w = spec["h"], spec["w"]
+    d = syn.make_depth(1, h, w, spec["kind"], seed=spec["seed"])[0, ..., 0]
+    if spec["stage"] == "blur":
+        d255 = d * np.float32(255)
+        L, R = sig.directional_motion_blur_gpu(torch.from_numpy(d255), spec["strength"], spec["thr"],
+                                               spec["strength"], falloff_exponent=spec["falloff"],
+                                               vert_smooth_px=spec["vert"])
+        return dict(crc=crc(d255), L=L.numpy(), R=R.numpy())
+    if spec["stage"] == "warp":
+        probe = syn.index_probe_image(h, w)
+        d255 = d * np.float32(255)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = sig.apply_stereo_divergence(probe, d255, spec["div"], spec["sep"], spec["expo"],
+                                              spec["fill"], spec["conv"])
+        return dict(crc=crc(probe, d255), out=np.asarray(out))
+    if spec["stage"] == "gpuwarp":
+        img = syn.make_image(1, h, w, seed=spec["seed"])
+        t = torch.from_numpy(img).permute(0, 3, 1, 2).contiguous()
+        warped, mask = sig.forward_warp_gpu(t, torch.from_numpy(d[None]), spec["div_px"], spec["sep_px"],
+                                            spec["expo"], spec["conv"])
+        return dict(crc=crc(img, d), warped=warped[0].numpy(), mask=mask[0].numpy().astype(np.uint8))
+    raise ValueError(spec["stage"])
+
+
+def main():
+    assert ref_loader.reference_available(), "needs /root/reference"
+    os.makedirs(GOLDEN, exist_ok=True)
+    manifest = {"node": [], "stage": []}
+    for spec in node_cases():
+        img, dep, outs, blur = run_node(spec)
+        is_gw = spec["params"]["fill_technique"] == 'GPU Warp (Fast)'
+        stereo, dl, dr, mask = outs
+        rec = dict(crc=crc(img, dep))
+        if is_gw:
+            rec.update(stereo=stereo.astype(np.float32), depth_l=dl[..., 0].astype(np.float32),
+                       depth_r=dr[..., 0].astype(np.float32), mask=(mask > 0).astype(np.uint8))
+        else:
+            q = lambda a: np.rint(a * 255.0).astype(np.uint8)
+            assert np.array_equal(q(stereo).astype(np.float32) / np.float32(255), stereo)
+            rec.update(stereo=q(stereo), depth_l=q(dl[..., 0]), depth_r=q(dr[..., 0]), mask=q(mask))
+            assert np.array_equal(dl[..., 0], dl[..., 1]) and np.array_equal(dl[..., 0], dl[..., 2])
+        if blur is not None:
+            rec.update(blur_l=blur[0], blur_r=blur[1])
+        np.savez_compressed(os.path.join(GOLDEN, f"node_{spec['name']}.npz"), **rec)
+        manifest["node"].append(spec)
+        print("node", spec["name"], [o.shape for o in outs])
+    for i, spec in enumerate(stage_cases()):
+        rec = run_stage(spec)
+        spec["name"] = f"{spec['stage']}_{i:03d}"
+        np.savez_compressed(os.path.join(GOLDEN, f"stage_{spec['name']}.npz"), **rec)
+        manifest["stage"].append(spec)
+    print("stage cases:", len(manifest["stage"]))
+    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
