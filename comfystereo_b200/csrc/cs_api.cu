@@ -1,0 +1,398 @@
+// cs_api.cu -- the C ABI (include/comfystereo_b200.h): argument checks, workspace carving, the
+// per-chunk kernel sequence of the hot path, and the host-buffer pipeline.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "cs_internal.cuh"
+
+namespace cs {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(CS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CS_CUDA(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+static bool is_cpu_technique(int fill) { return fill >= CS_FILL_NONE && fill <= CS_FILL_HYBRID_EDGE; }
+
+static int check_params(const cs_params* p) {
+    if (!p) return fail(CS_ERR_ARG, "params is NULL");
+    if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_GPU_WARP) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
+    if (p->mode < CS_MODE_LEFT_RIGHT || p->mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
+    if (p->blur_enabled) {
+        if (p->blur_box < 1) return fail(CS_ERR_UNSUPPORTED, "kernel size should be greater than zero");
+        if (p->blur_radius < 0 || p->blur_radius > kMaxBlurRadius)
+            return fail(CS_ERR_UNSUPPORTED, "blur radius %d outside 0..%d", p->blur_radius, kMaxBlurRadius);
+        if (p->blur_vert_smooth < 0) return fail(CS_ERR_ARG, "negative vert_smooth");
+    }
+    return CS_OK;
+}
+
+static void out_dims(int mode, int h, int w, int* ho, int* wo) {
+    *ho = h; *wo = w;
+    if (mode == CS_MODE_LEFT_RIGHT || mode == CS_MODE_RIGHT_LEFT) *wo = 2 * w;
+    if (mode == CS_MODE_TOP_BOTTOM || mode == CS_MODE_BOTTOM_TOP) *ho = 2 * h;
+}
+
+// Per-eye signed divergence / separation in pixels (SIG:1533-1541, SIG:1602-1603, SIG:1060-1065).
+static void eye_specs(const cs_params* p, int w, EyeSpec eye[2]) {
+    const double ldiv = p->divergence * (1 + p->stereo_balance);
+    const double rdiv = p->divergence * (1 - p->stereo_balance);
+    const double sep = p->separation;
+    eye[0].passthrough = ldiv < 0.001;
+    eye[1].passthrough = rdiv < 0.001;
+    if (p->fill == CS_FILL_GPU_WARP) {
+        const double ldiv_px = (ldiv / 100.0) * w, rdiv_px = (rdiv / 100.0) * w, sep_px = (sep / 100.0) * w;
+        eye[0].div_px = +ldiv_px; eye[0].sep_px = -sep_px;
+        eye[1].div_px = -rdiv_px; eye[1].sep_px = sep_px;
+    } else {
+        eye[0].div_px = ((+1 * ldiv) / 100.0) * w; eye[0].sep_px = ((-1 * sep) / 100.0) * w;
+        eye[1].div_px = ((-1 * rdiv) / 100.0) * w; eye[1].sep_px = (sep / 100.0) * w;
+    }
+}
+
+struct Workspace {
+    FrameStats* stats;
+    float* gray;
+    uint32_t* image_u8;
+    float* blur_l;
+    float* blur_r;
+    uint8_t* dist;
+    uint32_t* eye_out[2];
+    void* warp_scratch;
+    size_t warp_scratch_bytes;
+    size_t total;
+};
+
+static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) {
+    Workspace ws;
+    memset(&ws, 0, sizeof(ws));
+    const size_t px = (size_t)chunk * h * w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return (char*)base + o; };
+    ws.stats = (FrameStats*)take((size_t)chunk * sizeof(FrameStats));
+    ws.gray = (float*)take(px * 4);
+    const bool cpu = is_cpu_technique(p->fill);
+    if (cpu) ws.image_u8 = (uint32_t*)take(px * 4);
+    if (p->blur_enabled) {
+        ws.blur_l = (float*)take(px * 4);
+        ws.blur_r = (float*)take(px * 4);
+        ws.dist = (uint8_t*)take(px * 2);
+    }
+    if (cpu) {
+        ws.eye_out[0] = (uint32_t*)take(px * 4);
+        ws.eye_out[1] = (uint32_t*)take(px * 4);
+        if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP) {
+            ws.warp_scratch_bytes = polylines_scratch_bytes(chunk, h);
+            ws.warp_scratch = take(ws.warp_scratch_bytes);
+        }
+    }
+    ws.total = off;
+    return ws;
+}
+
+static cudaError_t launch_fill(const WarpArgs& a, cudaStream_t s) {
+    switch (a.fill) {
+        case CS_FILL_NONE: case CS_FILL_NAIVE: case CS_FILL_NAIVE_INTERP: case CS_FILL_INVERSE:
+            return launch_warp_rows(a, s);
+        case CS_FILL_POLYLINES_SOFT: case CS_FILL_POLYLINES_SHARP:
+            return launch_polylines(a, s);
+        case CS_FILL_HYBRID_EDGE:
+            return launch_hybrid(a, s);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+// One chunk of frames, all on `s`.  Pointers are already offset to the chunk's first frame.
+static int run_chunk(const cs_params* p, const float* image, const float* depth, int n, int h, int w, int c,
+                     float* stereo, float* depth_l, float* depth_r, float* mask, const Workspace& ws,
+                     int flags, cudaStream_t s) {
+    const bool cpu = is_cpu_technique(p->fill);
+    const int group = p->group_size > 0 ? p->group_size : n;
+    EyeSpec eye[2];
+    eye_specs(p, w, eye);
+    CS_CUDA(launch_init_stats(ws.stats, n, s), "init_stats");
+    if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP)
+        CS_CUDA(cudaMemsetAsync((char*)ws.warp_scratch + ws.warp_scratch_bytes - 16 * sizeof(int), 0, 16 * sizeof(int), s),
+                "memset status");
+    // N1 + L1 (+ O1 input side for the CPU techniques)
+    CS_CUDA(launch_prepare(cpu ? image : nullptr, depth, n, h, w, c, ws.gray, cpu ? ws.image_u8 : nullptr, ws.stats, s),
+            "prepare");
+    const float* dl = ws.gray;
+    const float* dr = ws.gray;
+    if (p->blur_enabled) {
+        // B1; CPU techniques decide x255 per frame (SIG:1475), GPU Warp per sub-batch (SIG:1045)
+        CS_CUDA(launch_blur(ws.gray, ws.stats, cpu ? 1 : 2, group, n, h, w, *p, ws.blur_l, ws.blur_r, ws.dist,
+                            cpu ? depth_l : nullptr, cpu ? depth_r : nullptr, s), "blur");
+        dl = ws.blur_l; dr = ws.blur_r;
+        if (!cpu) CS_CUDA(launch_depth_out(dl, dr, ws.stats, n, h, w, 1, 2, group, depth_l, depth_r, s), "depth_out");
+    } else {
+        CS_CUDA(launch_depth_out(dl, dr, ws.stats, n, h, w, 0, cpu ? 1 : 2, group, depth_l, depth_r, s), "depth_out");
+    }
+    if (cpu) {
+        WarpArgs a;
+        memset(&a, 0, sizeof(a));
+        a.image_u8 = ws.image_u8;
+        a.depth[0] = dl; a.depth[1] = dr;
+        a.stats = ws.stats;
+        a.use_blur_stats = p->blur_enabled ? 1 : 0;
+        a.scale_by_stats = p->blur_enabled ? 0 : 1;
+        a.out[0] = ws.eye_out[0]; a.out[1] = ws.eye_out[1];
+        a.n = n; a.h = h; a.w = w;
+        a.fill = p->fill;
+        a.eye[0] = eye[0]; a.eye[1] = eye[1];
+        a.expo = p->stereo_offset_exponent;
+        a.conv = (float)p->convergence_point;
+        a.scratch = ws.warp_scratch; a.scratch_bytes = ws.warp_scratch_bytes;
+        a.flags = flags;
+        if (!(eye[0].passthrough && eye[1].passthrough)) CS_CUDA(launch_fill(a, s), "warp/fill");
+        // an eye whose divergence is < 0.001 is the quantised input itself (SIG:1536, 1539)
+        const uint32_t* L = eye[0].passthrough ? ws.image_u8 : ws.eye_out[0];
+        const uint32_t* R = eye[1].passthrough ? ws.image_u8 : ws.eye_out[1];
+        CS_CUDA(launch_compose(L, R, n, h, w, p->mode, stereo, mask, s), "compose");
+    } else {
+        GpuWarpArgs g;
+        memset(&g, 0, sizeof(g));
+        g.image = image;
+        g.depth[0] = dl; g.depth[1] = dr;
+        g.stats = ws.stats;
+        g.use_blur_stats = p->blur_enabled ? 1 : 0;
+        g.prescale = 1;
+        g.group = group;
+        g.n = n; g.h = h; g.w = w; g.mode = p->mode;
+        g.eye[0] = eye[0]; g.eye[1] = eye[1];
+        g.expo = (float)p->stereo_offset_exponent;
+        g.conv = (float)p->convergence_point;
+        g.stereo = stereo; g.mask = mask;
+        CS_CUDA(launch_gpuwarp(g, s), "gpuwarp");
+    }
+    return CS_OK;
+}
+
+static int g_test_flags = 0;
+
+}  // namespace cs
+
+using namespace cs;
+
+extern "C" {
+
+int cs_abi_version(void) { return CS_ABI_VERSION; }
+const char* cs_last_error(void) { return g_err; }
+
+int cs_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(CS_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(CS_ERR_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(CS_ERR_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", dev, prop.major, prop.minor);
+    return CS_OK;
+}
+
+int cs_output_dims(const cs_params* p, int h, int w, int* ho, int* wo, int* hm, int* wm) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (h < 1 || w < 1 || !ho || !wo || !hm || !wm) return fail(CS_ERR_ARG, "bad dims");
+    out_dims(p->mode, h, w, ho, wo);
+    if (p->fill == CS_FILL_GPU_WARP) { *hm = h; *wm = w; }   // M2: single-eye shape even for SBS
+    else { *hm = *ho; *wm = *wo; }                           // M1: shape of the composed image
+    return CS_OK;
+}
+
+size_t cs_workspace_bytes(const cs_params* p, int chunk, int h, int w) {
+    if (!p || chunk < 1 || h < 1 || w < 1) return 0;
+    return carve(p, chunk, h, w, nullptr).total;
+}
+
+void cs_set_test_flags(int flags) { g_test_flags = flags; }
+
+long long cs_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int cs_depth_prepare(const float* depth, int n, int h, int w, int c, float* gray, float* minmax, void* stream) {
+    if (!depth || !gray || n < 1 || h < 1 || w < 1 || c < 1) return fail(CS_ERR_ARG, "cs_depth_prepare: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameStats* st = nullptr;
+    CS_CUDA(cudaMallocAsync((void**)&st, (size_t)n * sizeof(FrameStats), s), "cudaMallocAsync");
+    CS_CUDA(launch_init_stats(st, n, s), "init_stats");
+    CS_CUDA(launch_prepare(nullptr, depth, n, h, w, c, gray, nullptr, st, s), "prepare");
+    if (minmax) CS_CUDA(launch_export_stats(st, n, 0, minmax, 2, s), "export_stats");
+    CS_CUDA(cudaFreeAsync(st, s), "cudaFreeAsync");
+    return CS_OK;
+}
+
+int cs_blur(const float* depth255, int n, int h, int w, const cs_params* p, float* blur_l, float* blur_r,
+            float* minmax, uint8_t* dist_scratch, void* stream) {
+    if (!depth255 || !blur_l || !blur_r || !dist_scratch || !p || n < 1 || h < 1 || w < 1)
+        return fail(CS_ERR_ARG, "cs_blur: bad argument");
+    if (p->blur_box < 1) return fail(CS_ERR_UNSUPPORTED, "kernel size should be greater than zero");
+    if (p->blur_radius < 0 || p->blur_radius > kMaxBlurRadius) return fail(CS_ERR_UNSUPPORTED, "blur radius out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameStats* st = nullptr;
+    CS_CUDA(cudaMallocAsync((void**)&st, (size_t)n * sizeof(FrameStats), s), "cudaMallocAsync");
+    CS_CUDA(launch_init_stats(st, n, s), "init_stats");
+    CS_CUDA(launch_blur(depth255, st, 0, 1, n, h, w, *p, blur_l, blur_r, dist_scratch, nullptr, nullptr, s), "blur");
+    if (minmax) CS_CUDA(launch_export_stats(st, n, 1, minmax, 4, s), "export_stats");
+    CS_CUDA(cudaFreeAsync(st, s), "cudaFreeAsync");
+    return CS_OK;
+}
+
+int cs_shift_indices(const float* nd, int n, int h, int w, double div_px, double sep_px, double exponent,
+                     int kind, int32_t* out, void* stream) {
+    if (!nd || !out || n < 1 || h < 1 || w < 1 || kind < 0 || kind > 1) return fail(CS_ERR_ARG, "cs_shift_indices: bad argument");
+    CS_CUDA(launch_shift_indices(nd, n, h, w, div_px, sep_px, exponent, kind, out, (cudaStream_t)stream), "shift_indices");
+    return CS_OK;
+}
+
+size_t cs_warp_fill_scratch_bytes(int n, int h, int w) {
+    (void)w;
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(polylines_scratch_bytes(n, h));
+}
+
+int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int w, int fill, double divergence,
+                 double separation, double exponent, double convergence, uint8_t* out_u8, void* scratch,
+                 size_t scratch_bytes, void* stream) {
+    if (!image_u8 || !depth || !out_u8 || !scratch || n < 1 || h < 1 || w < 1)
+        return fail(CS_ERR_ARG, "cs_warp_fill: bad argument");
+    if (fill < CS_FILL_NONE || fill > CS_FILL_HYBRID_EDGE) return fail(CS_ERR_ARG, "cs_warp_fill: fill %d is not a CPU technique", fill);
+    if (scratch_bytes < cs_warp_fill_scratch_bytes(n, h, w)) return fail(CS_ERR_WORKSPACE, "cs_warp_fill: scratch too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameStats* st = (FrameStats*)scratch;
+    char* rest = (char*)scratch + align_up((size_t)n * sizeof(FrameStats));
+    CS_CUDA(launch_init_stats(st, n, s), "init_stats");
+    CS_CUDA(launch_minmax(depth, n, (int64_t)h * w, st, s), "minmax");
+    CS_CUDA(cudaMemsetAsync(rest, 0, polylines_scratch_bytes(n, h), s), "memset");
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.image_u8 = (const uint32_t*)image_u8;
+    a.depth[0] = depth; a.depth[1] = depth;
+    a.stats = st;
+    a.use_blur_stats = 0; a.scale_by_stats = 0;   // apply_stereo_divergence takes the depth as given
+    a.out[0] = (uint32_t*)out_u8; a.out[1] = nullptr;
+    a.n = n; a.h = h; a.w = w; a.fill = fill;
+    a.eye[0].div_px = (divergence / 100.0) * w;
+    a.eye[0].sep_px = (separation / 100.0) * w;
+    a.eye[0].passthrough = 0;
+    a.eye[1].passthrough = 1;
+    a.expo = exponent;
+    a.conv = (float)convergence;
+    a.scratch = rest; a.scratch_bytes = polylines_scratch_bytes(n, h);
+    a.flags = g_test_flags;
+    cudaError_t e = launch_fill(a, s);
+    if (e != cudaSuccess) return cuda_fail(e, "warp/fill");
+    return CS_OK;
+}
+
+int cs_forward_warp(const float* image, const float* depth, int n, int h, int w, double div_px, double sep_px,
+                    double exponent, double convergence, float* warped, float* mask, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+    if (!image || !depth || !warped || !mask || !scratch || n < 1 || h < 1 || w < 1)
+        return fail(CS_ERR_ARG, "cs_forward_warp: bad argument");
+    if (scratch_bytes < (size_t)n * sizeof(FrameStats)) return fail(CS_ERR_WORKSPACE, "cs_forward_warp: scratch too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameStats* st = (FrameStats*)scratch;
+    CS_CUDA(launch_init_stats(st, n, s), "init_stats");
+    CS_CUDA(launch_minmax(depth, n, (int64_t)h * w, st, s), "minmax");
+    GpuWarpArgs g;
+    memset(&g, 0, sizeof(g));
+    g.image = image;
+    g.depth[0] = depth; g.depth[1] = depth;
+    g.stats = st;
+    g.use_blur_stats = 0; g.prescale = 0; g.group = n;   // SIG:314-316: "/255 if ANY frame of the batch has max > 1"
+    g.n = n; g.h = h; g.w = w; g.mode = CS_MODE_LEFT_ONLY;
+    g.eye[0].div_px = div_px; g.eye[0].sep_px = sep_px; g.eye[0].passthrough = 0;
+    g.eye[1].passthrough = 1;
+    g.expo = (float)exponent; g.conv = (float)convergence;
+    g.stereo = warped; g.mask = mask;
+    CS_CUDA(launch_gpuwarp(g, s), "gpuwarp");
+    return CS_OK;
+}
+
+int cs_quantize_image(const float* image, int n, int h, int w, uint8_t* image_u8, void* stream) {
+    if (!image || !image_u8 || n < 1 || h < 1 || w < 1) return fail(CS_ERR_ARG, "cs_quantize_image: bad argument");
+    CS_CUDA(launch_quantize(image, (int64_t)n * h * w, (uint32_t*)image_u8, (cudaStream_t)stream), "quantize");
+    return CS_OK;
+}
+
+int cs_compose(const uint8_t* left_u8, const uint8_t* right_u8, int n, int h, int w, int mode, float* stereo,
+               float* mask, void* stream) {
+    if (!left_u8 || !right_u8 || !stereo || !mask || n < 1 || h < 1 || w < 1) return fail(CS_ERR_ARG, "cs_compose: bad argument");
+    if (mode < CS_MODE_LEFT_RIGHT || mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
+    CS_CUDA(launch_compose((const uint32_t*)left_u8, (const uint32_t*)right_u8, n, h, w, mode, stereo, mask,
+                           (cudaStream_t)stream), "compose");
+    return CS_OK;
+}
+
+int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, int n, int h, int w, int c,
+                    float* stereo, float* depth_l, float* depth_r, float* mask, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!image || !depth || !stereo || !depth_l || !depth_r || !mask || !workspace)
+        return fail(CS_ERR_ARG, "cs_stereo_batch: NULL pointer");
+    if (n < 1 || h < 1 || w < 2 || c < 1) return fail(CS_ERR_ARG, "cs_stereo_batch: bad size n=%d h=%d w=%d c=%d", n, h, w, c);
+    if ((uintptr_t)workspace % 256) return fail(CS_ERR_ARG, "cs_stereo_batch: workspace must be 256-byte aligned");
+    const bool cpu = is_cpu_technique(p->fill);
+    if (cpu && c != 1 && c != 3) return fail(CS_ERR_ARG, "cs_stereo_batch: depth must have 1 or 3 channels");
+    // largest chunk that fits; GPU Warp couples frames inside a sub-batch (Q9), so chunks are whole sub-batches
+    const int group = (!cpu && p->group_size > 0) ? (p->group_size < n ? p->group_size : n) : 1;
+    const size_t per = cs_workspace_bytes(p, group, h, w);
+    if (per == 0 || workspace_bytes < per)
+        return fail(CS_ERR_WORKSPACE, "cs_stereo_batch: workspace %zu B < %zu B needed for %d frame(s)", workspace_bytes, per, group);
+    int chunk = group;
+    while (chunk + group <= n && cs_workspace_bytes(p, chunk + group, h, w) <= workspace_bytes) chunk += group;
+    int ho, wo, hm, wm;
+    cs_output_dims(p, h, w, &ho, &wo, &hm, &wm);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int m = (n - f0 < chunk) ? n - f0 : chunk;
+        Workspace ws = carve(p, m, h, w, workspace);
+        const size_t px = (size_t)h * w;
+        rc = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * px * c, m, h, w, c,
+                       stereo + (size_t)f0 * ho * wo * 3, depth_l + (size_t)f0 * px * 3, depth_r + (size_t)f0 * px * 3,
+                       mask + (size_t)f0 * hm * wm, ws, g_test_flags, s);
+        if (rc) return rc;
+    }
+    return CS_OK;
+}
+
+int cs_polylines_status(const cs_params* p, int chunk, int h, int w, const void* workspace, int* status_out, int* flagged_rows) {
+    // Debug/telemetry: reads back the status word and the number of rows that needed the exact replay
+    // in the most recent chunk.  Synchronous.
+    if (!p || !workspace) return fail(CS_ERR_ARG, "cs_polylines_status: bad argument");
+    Workspace ws = carve(p, chunk, h, w, const_cast<void*>(workspace));
+    if (!ws.warp_scratch) return fail(CS_ERR_ARG, "cs_polylines_status: not a polylines configuration");
+    const size_t nflags = (size_t)chunk * 2 * h;
+    int* host = (int*)malloc((nflags + 16) * sizeof(int));
+    if (!host) return fail(CS_ERR_ARG, "out of host memory");
+    cudaError_t e = cudaMemcpy(host, ws.warp_scratch, (nflags + 16) * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(host); return cuda_fail(e, "cudaMemcpy"); }
+    int cnt = 0;
+    for (size_t i = 0; i < nflags; ++i) cnt += host[i] != 0;
+    if (status_out) *status_out = host[nflags];
+    if (flagged_rows) *flagged_rows = cnt;
+    free(host);
+    return CS_OK;
+}
+
+}  // extern "C"

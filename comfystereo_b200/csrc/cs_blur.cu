@@ -1,0 +1,273 @@
+// cs_blur.cu -- B1: the edge-aware directional depth blur (SIG:1171-1251, SIG:1131-1168).
+//
+// Two kernels per chunk of frames:
+//   k_edge_dist   one CTA per image row: 3x3 Sobel-x (zero padded), the two threshold masks as
+//                 bit words in shared memory (warp ballots), then per pixel the distance to the
+//                 nearest mask bit left/right (clz/ffs over at most R/32+2 words), saturated at
+//                 R+1 and stored as uint8 -> 2 B/px of scratch instead of two float weight maps.
+//   k_blur_blend  persistent CTAs over 256-pixel row segments: vertical (2v+1)-tap mean of the
+//                 LUT weights, bs-tap box mean of the depth row staged in shared memory, blend,
+//                 per-frame min/max of both results, and (CPU techniques) the depth outputs.
+//
+// Summation order is fixed (ascending tap, fmaf) and identical to oracle/stereo_oracle.c, so
+// CUDA and oracle agree bit for bit; torch's own conv2d order is unspecified.
+//
+// Bytes per pixel: k_edge_dist reads gray 4 B (x3 rows, L1/L2 hits) and writes 2 B;
+// k_blur_blend reads gray 4 B + (2v+1) x 2 B of distances (L1/L2 hits), writes 8 B of blurred
+// depth scratch and, for CPU techniques, 24 B of depth outputs (streamed, evict-first).
+#include "cs_internal.cuh"
+
+namespace cs {
+
+struct BlurLut {
+    float w[256];  // weight for distance k = 0..R+1
+};
+
+__device__ __forceinline__ float frame_scale(const FrameStats* st, int frame, int scale_mode,
+                                             int group, int n) {
+    if (scale_mode == 0) return 1.0f;
+    float gm;
+    if (scale_mode == 1) gm = ord2f(st[frame].gray_max);
+    else {
+        int g0 = (frame / group) * group, g1 = min(g0 + group, n);
+        gm = -INFINITY;
+        for (int f = g0; f < g1; ++f) gm = fmaxf(gm, ord2f(st[f].gray_max));
+    }
+    return (gm <= 1.0f) ? 255.0f : 1.0f;
+}
+
+__device__ __forceinline__ float scaled(float g, float scale) {
+    return scale == 1.0f ? g : g * scale;
+}
+
+// ------------------------------------------------------------------------------------ dist
+__global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gray,
+                                                   const FrameStats* __restrict__ st, int scale_mode,
+                                                   int group, int n, int h, int w, float edge_div,
+                                                   int radius, uint8_t* __restrict__ dist_l,
+                                                   uint8_t* __restrict__ dist_r) {
+    extern __shared__ uint32_t s_bits[];  // [2][nwords]
+    const int y = blockIdx.x, frame = blockIdx.y;
+    const int nwords = (w + 31) >> 5;
+    uint32_t* bl = s_bits;
+    uint32_t* br = s_bits + nwords;
+    const float scale = frame_scale(st, frame, scale_mode, group, n);
+    const float* base = gray + (int64_t)frame * h * w;
+    const float* r0 = (y > 0) ? base + (int64_t)(y - 1) * w : nullptr;
+    const float* r1 = base + (int64_t)y * w;
+    const float* r2 = (y + 1 < h) ? base + (int64_t)(y + 1) * w : nullptr;
+
+    const int wpad = nwords << 5;
+    for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
+        bool ml = false, mr = false;
+        if (x < w) {
+            float g = 0.0f;
+            const bool hasl = x > 0, hasr = x + 1 < w;
+            if (r0) {
+                float l = hasl ? scaled(r0[x - 1], scale) : 0.0f, r = hasr ? scaled(r0[x + 1], scale) : 0.0f;
+                g = fmaf(-1.0f, l, g);
+                g = fmaf(1.0f, r, g);
+            }
+            {
+                float l = hasl ? scaled(r1[x - 1], scale) : 0.0f, r = hasr ? scaled(r1[x + 1], scale) : 0.0f;
+                g = fmaf(-2.0f, l, g);
+                g = fmaf(2.0f, r, g);
+            }
+            if (r2) {
+                float l = hasl ? scaled(r2[x - 1], scale) : 0.0f, r = hasr ? scaled(r2[x + 1], scale) : 0.0f;
+                g = fmaf(-1.0f, l, g);
+                g = fmaf(1.0f, r, g);
+            }
+            float e = fabsf(g) / edge_div;          // IEEE float32 division, SIG:1217
+            e = fminf(fmaxf(e, 0.0f), 1.0f);
+            ml = (g > 0.0f) && (e > 0.5f);
+            mr = (g < 0.0f) && (e > 0.5f);
+        }
+        uint32_t wl = __ballot_sync(0xffffffffu, ml), wr = __ballot_sync(0xffffffffu, mr);
+        if ((threadIdx.x & 31) == 0) { bl[x >> 5] = wl; br[x >> 5] = wr; }
+    }
+    __syncthreads();
+
+    const int far = radius + 1;
+    uint8_t* ol = dist_l + ((int64_t)frame * h + y) * w;
+    uint8_t* orr = dist_r + ((int64_t)frame * h + y) * w;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        const int wi = x >> 5, b = x & 31;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t* bits = pass ? br : bl;
+            int d = far;
+            // nearest set bit at or left of x
+            uint32_t m = bits[wi] & (0xffffffffu >> (31 - b));
+            if (m) d = min(d, b - (31 - __clz(m)));
+            else {
+                for (int k = 1; wi - k >= 0 && (b + 32 * (k - 1) + 1) <= radius; ++k) {
+                    uint32_t q = bits[wi - k];
+                    if (q) { d = min(d, b + 32 * k - (31 - __clz(q))); break; }
+                }
+            }
+            // nearest set bit at or right of x
+            m = bits[wi] & (0xffffffffu << b);
+            if (m) d = min(d, (__ffs(m) - 1) - b);
+            else {
+                for (int k = 1; wi + k < nwords && (32 * (k - 1) + (32 - b)) <= radius; ++k) {
+                    uint32_t q = bits[wi + k];
+                    if (q) { d = min(d, 32 * k - b + (__ffs(q) - 1)); break; }
+                }
+            }
+            (pass ? orr : ol)[x] = (uint8_t)d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ blend
+constexpr int kSeg = 256;  // pixels per work item = threads per CTA
+
+__global__ void __launch_bounds__(kSeg) k_blur_blend(
+    const float* __restrict__ gray, FrameStats* __restrict__ st, int scale_mode, int group, int n,
+    int h, int w, int bs, int radius, int v, const __grid_constant__ BlurLut lut,
+    const uint8_t* __restrict__ dist_l, const uint8_t* __restrict__ dist_r, float* __restrict__ blur_l,
+    float* __restrict__ blur_r, float* __restrict__ out_l, float* __restrict__ out_r, int items_per_frame,
+    int segs_per_row) {
+    extern __shared__ float s_row[];  // [kSeg + bs] depth row segment with halo, then 2*kSeg output staging
+    float* s_vl = s_row + kSeg + bs;
+    float* s_vr = s_vl + kSeg;
+    __shared__ float s_red[4][kSeg / 32];
+    const int frame = blockIdx.y;
+    const float scale = frame_scale(st, frame, scale_mode, group, n);
+    const float wv = 1.0f / (float)(2 * v + 1);
+    const float wb = 1.0f / (float)bs;
+    const int lo = bs / 2;
+    const uint64_t pol = policy_evict_first();
+    const float* base = gray + (int64_t)frame * h * w;
+    const uint8_t* dl = dist_l + (int64_t)frame * h * w;
+    const uint8_t* dr = dist_r + (int64_t)frame * h * w;
+    const bool vec_out = out_l && (w % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0);
+
+    float mnl = INFINITY, mxl = -INFINITY, mnr = INFINITY, mxr = -INFINITY;
+    for (int item = blockIdx.x; item < items_per_frame; item += gridDim.x) {
+        const int y = item / segs_per_row, x0 = (item - y * segs_per_row) * kSeg;
+        const float* row = base + (int64_t)y * w;
+        // stage depth[x0 - lo .. x0 + kSeg + bs - lo) (zeros outside the row)
+        for (int i = threadIdx.x; i < kSeg + bs; i += kSeg) {
+            int xx = x0 - lo + i;
+            s_row[i] = (xx >= 0 && xx < w) ? scaled(row[xx], scale) : 0.0f;
+        }
+        __syncthreads();
+        const int x = x0 + threadIdx.x;
+        float vl = 0.0f, vr = 0.0f;
+        if (x < w) {
+            float wl, wr;
+            if (v > 0) {
+                wl = 0.0f; wr = 0.0f;
+                const int y0 = max(y - v, 0), y1 = min(y + v, h - 1);
+                for (int yy = y0; yy <= y1; ++yy) {
+                    wl = fmaf(lut.w[dl[(int64_t)yy * w + x]], wv, wl);
+                    wr = fmaf(lut.w[dr[(int64_t)yy * w + x]], wv, wr);
+                }
+            } else {
+                wl = lut.w[dl[(int64_t)y * w + x]];
+                wr = lut.w[dr[(int64_t)y * w + x]];
+            }
+            float b = 0.0f;
+            for (int k = 0; k < bs; ++k) b = fmaf(s_row[threadIdx.x + k], wb, b);
+            const float d = s_row[threadIdx.x + lo];
+            float t0 = wl * b, t1 = (1.0f - wl) * d;
+            vl = t0 + t1;
+            t0 = wr * b; t1 = (1.0f - wr) * d;
+            vr = t0 + t1;
+            blur_l[((int64_t)frame * h + y) * w + x] = vl;
+            blur_r[((int64_t)frame * h + y) * w + x] = vr;
+            mnl = fminf(mnl, vl); mxl = fmaxf(mxl, vl);
+            mnr = fminf(mnr, vr); mxr = fmaxf(mxr, vr);
+        }
+        if (out_l) {  // CPU-technique depth outputs: u8 = trunc(v*255) mod 256, /255, x3 channels (Q1)
+            long long il = (long long)(vl * 255.0f), ir = (long long)(vr * 255.0f);
+            s_vl[threadIdx.x] = (float)(int)(il & 255) / 255.0f;
+            s_vr[threadIdx.x] = (float)(int)(ir & 255) / 255.0f;
+            __syncthreads();
+            const int npx = min(kSeg, w - x0);
+            float* pl = out_l + (((int64_t)frame * h + y) * w + x0) * 3;
+            float* pr = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
+            if (vec_out) {
+                const int nvec = (npx * 3) >> 2;  // npx % 4 == 0 here
+                for (int m = threadIdx.x; m < nvec; m += kSeg) {
+                    int f0 = 4 * m;
+                    float4 a = make_float4(s_vl[f0 / 3], s_vl[(f0 + 1) / 3], s_vl[(f0 + 2) / 3], s_vl[(f0 + 3) / 3]);
+                    float4 c = make_float4(s_vr[f0 / 3], s_vr[(f0 + 1) / 3], s_vr[(f0 + 2) / 3], s_vr[(f0 + 3) / 3]);
+                    st_stream_f4(reinterpret_cast<float4*>(pl) + m, a, pol);
+                    st_stream_f4(reinterpret_cast<float4*>(pr) + m, c, pol);
+                }
+            } else {
+                for (int f = threadIdx.x; f < npx * 3; f += kSeg) { pl[f] = s_vl[f / 3]; pr[f] = s_vr[f / 3]; }
+            }
+        }
+        __syncthreads();
+    }
+    mnl = warp_min(mnl); mxl = warp_max(mxl); mnr = warp_min(mnr); mxr = warp_max(mxr);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_red[0][wid] = mnl; s_red[1][wid] = mxl; s_red[2][wid] = mnr; s_red[3][wid] = mxr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kSeg / 32; ++k) {
+            mnl = fminf(mnl, s_red[0][k]); mxl = fmaxf(mxl, s_red[1][k]);
+            mnr = fminf(mnr, s_red[2][k]); mxr = fmaxf(mxr, s_red[3][k]);
+        }
+        if (mnl <= mxl) {
+            atomicMin(&st[frame].l_min, f2ord(mnl)); atomicMax(&st[frame].l_max, f2ord(mxl));
+            atomicMin(&st[frame].r_min, f2ord(mnr)); atomicMax(&st[frame].r_max, f2ord(mxr));
+        }
+    }
+}
+
+// weight(dist) = clamp(1 - dist/R, 0, 1) ** falloff, float32 (SIG:1168).  Built on the host once
+// per call (<= 256 entries): torch.pow special-cases exponents 1, 2, 3, 0.5; otherwise powf.
+static void build_lut(BlurLut& lut, int radius, float falloff) {
+    for (int k = 0; k < 256; ++k) {
+        float q = (float)k / (float)radius;   // radius 0 -> NaN at k = 0, inf elsewhere (quirk Q11)
+        float wgt = 1.0f - q;
+        if (wgt == wgt) {
+            if (wgt < 0.0f) wgt = 0.0f;
+            if (wgt > 1.0f) wgt = 1.0f;
+            if (falloff == 1.0f) {}
+            else if (falloff == 2.0f) wgt = wgt * wgt;
+            else if (falloff == 3.0f) wgt = (wgt * wgt) * wgt;
+            else if (falloff == 0.5f) wgt = sqrtf(wgt);
+            else wgt = powf(wgt, falloff);
+        }
+        lut.w[k] = wgt;
+    }
+}
+
+cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, int group, int n, int h,
+                        int w, const cs_params& p, float* blur_l, float* blur_r, uint8_t* dist,
+                        float* depth_l_out, float* depth_r_out, cudaStream_t s) {
+    const int bs = p.blur_box, radius = p.blur_radius, v = p.blur_vert_smooth;
+    if (bs < 1 || radius < 0 || radius > kMaxBlurRadius || v < 0) return cudaErrorInvalidValue;
+    uint8_t* dist_l = dist;
+    uint8_t* dist_r = dist + (int64_t)n * h * w;
+    const float edge_div = (float)(10.0 * p.blur_edge_threshold);  // python float 10*thr -> float32 scalar
+    const int nwords = (w + 31) >> 5;
+    k_edge_dist<<<dim3(h, n), 256, 2 * nwords * sizeof(uint32_t), s>>>(
+        gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    BlurLut lut;
+    build_lut(lut, radius, (float)p.blur_falloff);
+    const int segs = (w + kSeg - 1) / kSeg;
+    const int items = segs * h;
+    // few CTAs per frame so the 4 min/max atomics per CTA stay cheap; >= 4 waves in total
+    int per_frame = (148 * 8 * 4 + n - 1) / n;
+    if (per_frame > items) per_frame = items;
+    if (per_frame < 1) per_frame = 1;
+    size_t smem = (size_t)(kSeg + bs + 2 * kSeg) * sizeof(float);
+    k_blur_blend<<<dim3(per_frame, n), kSeg, smem, s>>>(gray, stats, scale_mode, group < 1 ? 1 : group, n, h,
+                                                       w, bs, radius, v, lut, dist_l, dist_r, blur_l,
+                                                       blur_r, depth_l_out, depth_r_out, items, segs);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace cs

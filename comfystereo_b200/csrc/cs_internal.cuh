@@ -1,0 +1,188 @@
+// cs_internal.cuh -- shared device helpers and launcher declarations (sm_100a only).
+//
+// Arithmetic contract: the library is compiled with -fmad=false, so every float/double
+// multiply and add below rounds separately exactly like the reference's numba / numpy /
+// torch-CPU elementwise code.  Where a fused multiply-add is part of the defined arithmetic
+// (the three blur convolutions, the bilinear sample) it is written explicitly as fmaf().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/comfystereo_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "comfystereo_b200 targets sm_100a (B200) only"
+#endif
+
+namespace cs {
+
+constexpr int kMaxBlurRadius = 254;  // dist scratch is uint8: R + 1 must fit
+
+// ---------------------------------------------------------------- per-frame statistics
+// Monotone float <-> int encoding so that atomicMin/atomicMax on ints order floats.
+__host__ __device__ inline int f2ord(float f) {
+#ifdef __CUDA_ARCH__
+    int b = __float_as_int(f);
+#else
+    int b; memcpy(&b, &f, 4);
+#endif
+    return b >= 0 ? b : (b ^ 0x7FFFFFFF);
+}
+__host__ __device__ inline float ord2f(int o) {
+    int b = o >= 0 ? o : (o ^ 0x7FFFFFFF);
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+struct FrameStats {     // one per frame in the chunk, lives in the workspace
+    int gray_min, gray_max;  // of the gray depth as given (before the x255 decision)
+    int l_min, l_max;        // of the depth the LEFT eye warps with (0..255 scale)
+    int r_min, r_max;        // same, right eye
+    int pad0, pad1;
+};
+
+// ---------------------------------------------------------------- streaming memory access
+// Inputs/outputs are touched exactly once: keep them from displacing the L2-resident scratch.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_min(float v) {
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- shared arithmetic
+// sign_d * (abs(d) ** exponent) * divergence_px in float64, sign(0) = +1 (e.g. SIG:1863-1865).
+// pow(x, 2) and pow(x, 1) are exact in libm; they are special-cased so that the two common
+// exponents are bit-identical to the reference; other exponents use CUDA's pow (<= 2 ulp).
+__device__ __forceinline__ double signed_pow_offset(float nd, double expo, double div_px) {
+    double a = (double)fabsf(nd);
+    double p;
+    if (expo == 2.0) p = a * a;
+    else if (expo == 1.0) p = a;
+    else p = pow(a, expo);
+    double sp = (nd >= 0.0f) ? p : -p;
+    return sp * div_px;
+}
+
+// nd = (d - min) / (max - min) - conv  (numpy float32, SIG:1591-1600); flat frame -> 0 - conv.
+struct Normalizer {
+    float mn, range, conv;
+    int flat;
+    __device__ __forceinline__ float operator()(float d) const {
+        float q = flat ? 0.0f : (d - mn) / range;
+        return q - conv;
+    }
+};
+__device__ __forceinline__ Normalizer make_normalizer(int ord_min, int ord_max, float scale, float conv) {
+    // min/max are tracked on the unscaled values; x*255 is monotone so scaling commutes.
+    Normalizer n;
+    float lo = ord2f(ord_min) * scale, hi = ord2f(ord_max) * scale;
+    n.mn = lo; n.range = hi - lo; n.conv = conv; n.flat = (hi == lo);
+    return n;
+}
+
+// uint8 pixel packed RGBX in one 32-bit word (R lowest byte).
+__device__ __forceinline__ uint32_t pack_rgbx(int r, int g, int b, int x = 0) {
+    return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)x << 24);
+}
+
+// ---------------------------------------------------------------- launchers (host)
+struct EyeSpec {          // one eye of one call
+    double div_px, sep_px; // signed, in pixels (SIG:1602-1603)
+    int passthrough;       // divergence*(1 +- balance) < 0.001 -> the eye is the input image
+};
+
+struct WarpArgs {
+    const uint32_t* image_u8;   // [n][h][w] RGBX
+    const float* depth[2];      // per eye [n][h][w]; unscaled gray or blurred (see scale[])
+    const FrameStats* stats;    // [n]
+    int use_blur_stats;         // 1: l_/r_ min/max, 0: gray min/max
+    int scale_by_stats;         // 1: multiply depth by 255 when the frame's gray max <= 1 (blur off path)
+    uint32_t* out[2];           // per eye [n][h][w] RGBX (X = "filled" flag where meaningful)
+    int n, h, w;
+    int fill;
+    EyeSpec eye[2];
+    double expo;
+    float conv;
+    void* scratch;              // technique-specific device scratch
+    size_t scratch_bytes;
+    int flags;                  // bit 0: polylines -- skip the fast sweep, replay every row exactly (tests)
+};
+
+void count_launch();
+int fail(int code, const char* fmt, ...);   // records the thread-local cs_last_error() text, returns code
+cudaError_t launch_init_stats(FrameStats* stats, int n, cudaStream_t s);
+cudaError_t launch_prepare(const float* image, const float* depth, int n, int h, int w, int c,
+                           float* gray, uint32_t* image_u8, FrameStats* stats, cudaStream_t s);
+// scale_mode 0: input already 0..255; 1: x255 when the frame's gray max <= 1 (SIG:1475);
+//            2: same test over the frame's sub-batch of `group` frames (SIG:1045)
+// depth_l_out/depth_r_out (optional): the CPU-technique depth outputs (wrap quirk Q1), [n][h][w][3]
+cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, int group,
+                        int n, int h, int w, const cs_params& p, float* blur_l, float* blur_r,
+                        uint8_t* dist, float* depth_l_out, float* depth_r_out, cudaStream_t s);
+cudaError_t launch_depth_out(const float* src_l, const float* src_r, const FrameStats* stats, int n,
+                             int h, int w, int src_kind, int out_kind, int group, float* out_l,
+                             float* out_r, cudaStream_t s);
+cudaError_t launch_quantize(const float* image, int64_t total_px, uint32_t* out, cudaStream_t s);
+cudaError_t launch_shift_indices(const float* nd, int n, int h, int w, double div_px, double sep_px,
+                                 double expo, int kind, int32_t* out, cudaStream_t s);
+cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s);       // none / naive / interp / inverse
+cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s);       // soft / sharp
+cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s);          // hybrid_edge (2 kernels)
+size_t polylines_scratch_bytes(int n, int h);
+cudaError_t launch_minmax(const float* src, int n, int64_t npx, FrameStats* stats, cudaStream_t s);
+cudaError_t launch_export_stats(const FrameStats* stats, int n, int which, float* out, int stride, cudaStream_t s);
+cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, int h, int w, int mode,
+                           float* stereo, float* mask, cudaStream_t s);
+
+struct GpuWarpArgs {
+    const float* image;        // [n][h][w][3] float32
+    const float* depth[2];     // per eye [n][h][w], 0..255 scale or as given
+    const FrameStats* stats;
+    int use_blur_stats;        // 1: depth[] are the blurred maps (0..255 scale), stats l_/r_ fields
+    int prescale;              // use_blur_stats == 0 only.  1: depth *= 255 when the sub-batch max <= 1 (SIG:1045)
+                               //                            0: depth used as given (function-level call)
+    int group;                 // sub-batch size for the coupled range tests (Q9)
+    int n, h, w, mode;
+    EyeSpec eye[2];
+    float expo, conv;
+    float* stereo;             // final layout
+    float* mask;               // [n][h][w]
+};
+cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s);
+
+}  // namespace cs

@@ -1,0 +1,231 @@
+// cs_warp.cu -- W1 + F0/F1/F2 (apply_stereo_divergence_naive, SIG:1850-1910) and
+// I (apply_stereo_divergence_inverse, SIG:1715-1737).
+//
+// One CTA per (image row, frame, eye).  Disparity is purely horizontal, so a row is a closed
+// problem that lives in shared memory:
+//   sweep     every source pixel computes its destination column in FP64 and claims it with a
+//             shared-memory atomic.  The reference's sequential sweep ("last writer wins",
+//             right->left for div_px >= 0, left->right otherwise) is exactly "smallest source
+//             column wins" / "largest source column wins" (SURVEY.md 8a, W1); its z-buffer
+//             variant (inverse) is "largest nd wins, ties to the smallest source column",
+//             a 64-bit packed key.
+//   resolve   every destination pixel gathers its winner's colour from the RGBX8 row.
+//   fill      'naive': nearest filled pixel right-then-left within |int(div_px)|+1, found with
+//             clz/ffs over a bit map of the filled flags (reads the pre-fill row, SIG:1893-1908);
+//             'naive_interpolating': the reference's left-to-right gap walk has a true chain
+//             dependency through uint8 wrap-around (Q5), so one thread replays it on the row in
+//             shared memory (rows still run in parallel across CTAs).
+//
+// Bytes per pixel and eye: depth 4 B + RGBX8 4 B read (L2-resident scratch), RGBX8 4 B written.
+#include "cs_internal.cuh"
+
+namespace cs {
+
+__device__ __forceinline__ float eye_depth(const WarpArgs& a, int eye, int frame, int64_t off, float scale) {
+    float d = a.depth[eye][(int64_t)frame * a.h * a.w + off];
+    return scale == 1.0f ? d : d * scale;
+}
+
+// Per-(frame, eye) normaliser from the statistics block (D1, SIG:1586-1600).
+__device__ __forceinline__ Normalizer eye_normalizer(const WarpArgs& a, int eye, int frame, float* scale_out) {
+    const FrameStats st = a.stats[frame];
+    float scale = 1.0f;
+    int lo, hi;
+    if (a.use_blur_stats) {
+        lo = eye ? st.r_min : st.l_min;
+        hi = eye ? st.r_max : st.l_max;
+    } else {
+        lo = st.gray_min; hi = st.gray_max;
+        if (a.scale_by_stats && ord2f(st.gray_max) <= 1.0f) scale = 255.0f;   // SIG:1475-1476
+    }
+    *scale_out = scale;
+    return make_normalizer(lo, hi, scale, a.conv);
+}
+
+// distance (> 0) to the nearest set bit strictly right / left of x, or a large number
+__device__ __forceinline__ int bit_dist_right(const uint32_t* bits, int nwords, int x, int limit) {
+    int p = x + 1;
+    int wi = p >> 5;
+    if (wi >= nwords) return 1 << 30;
+    uint32_t m = bits[wi] & (0xffffffffu << (p & 31));
+    while (true) {
+        if (m) return (wi << 5) + (__ffs(m) - 1) - x;
+        ++wi;
+        if (wi >= nwords || (wi << 5) - x > limit) return 1 << 30;
+        m = bits[wi];
+    }
+}
+__device__ __forceinline__ int bit_dist_left(const uint32_t* bits, int x, int limit) {
+    int p = x - 1;
+    if (p < 0) return 1 << 30;
+    int wi = p >> 5;
+    uint32_t m = bits[wi] & (0xffffffffu >> (31 - (p & 31)));
+    while (true) {
+        if (m) return x - ((wi << 5) + 31 - __clz(m));
+        --wi;
+        if (wi < 0 || x - ((wi << 5) + 31) > limit) return 1 << 30;
+        m = bits[wi];
+    }
+}
+
+__device__ __forceinline__ int px_sum(uint32_t p) { return (int)(p & 255) + (int)((p >> 8) & 255) + (int)((p >> 16) & 255); }
+
+template <int FILL>  // CS_FILL_NONE / NAIVE / NAIVE_INTERP / INVERSE
+__global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
+    if (a.eye[eye].passthrough) return;
+    const int nwords = (w + 31) >> 5;
+    const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
+    float scale;
+    const Normalizer norm = eye_normalizer(a, eye, frame, &scale);
+    const int64_t row_off = (int64_t)y * w;
+    const uint32_t* img = a.image_u8 + (int64_t)frame * a.h * w + row_off;
+    uint32_t* out = a.out[eye] + (int64_t)frame * a.h * w + row_off;
+
+    if (FILL == CS_FILL_INVERSE) {
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
+        for (int x = threadIdx.x; x < w; x += blockDim.x) key[x] = 0ull;
+        __syncthreads();
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            float nd = norm(eye_depth(a, eye, frame, row_off + x, scale)) + 0.0f;
+            if (!(nd > -1.0f)) continue;  // z-buffer starts at -1 and the test is strict (SIG:1722, 1731)
+            double off = signed_pow_offset(nd, a.expo, div_px);
+            double dx = ((double)x + 0.5) + off;
+            dx = dx + sep_px;
+            int j = (int)floor(dx);
+            // larger nd wins, ties go to the smaller source column (ascending sweep + strict '>')
+            unsigned long long k = ((unsigned long long)((uint32_t)f2ord(nd) ^ 0x80000000u) << 32) |
+                                   (unsigned long long)(0xFFFFFFFFu - (uint32_t)x);
+            if (j >= 0 && j < w) atomicMax(&key[j], k);
+            if (j + 1 >= 0 && j + 1 < w) atomicMax(&key[j + 1], k);
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            unsigned long long k = key[x];
+            uint32_t px = 0;
+            if (k) px = (img[0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull)] & 0x00FFFFFFu) | 0x01000000u;
+            out[x] = px;
+        }
+        return;
+    } else {
+        int* win = reinterpret_cast<int*>(smem_raw);
+        uint32_t* bits = reinterpret_cast<uint32_t*>(win + w);
+        uint32_t* row = bits + nwords;  // only FILL == NAIVE_INTERP
+        const bool take_min = !(div_px < 0);
+        const int empty = take_min ? 0x7FFFFFFF : -1;
+        for (int x = threadIdx.x; x < w; x += blockDim.x) win[x] = empty;
+        __syncthreads();
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            float nd = norm(eye_depth(a, eye, frame, row_off + x, scale));
+            double off = signed_pow_offset(nd, a.expo, div_px);
+            double t = off + sep_px;
+            int cd = x + (int)t;  // truncation toward zero, SIG:1865
+            if (cd >= 0 && cd < w) {
+                if (take_min) atomicMin(&win[cd], x); else atomicMax(&win[cd], x);
+            }
+        }
+        __syncthreads();
+        const int wpad = nwords << 5;
+        for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
+            bool f = (x < w) && (win[x] != empty);
+            uint32_t b = __ballot_sync(0xffffffffu, f);
+            if ((threadIdx.x & 31) == 0) bits[x >> 5] = b;
+        }
+        __syncthreads();
+        if (FILL == CS_FILL_NONE) {
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                int s = win[x];
+                out[x] = (s != empty) ? ((img[s] & 0x00FFFFFFu) | 0x01000000u) : 0u;
+            }
+        } else if (FILL == CS_FILL_NAIVE) {
+            double adiv = fabs(div_px);
+            const int reach = (int)adiv + 1;  // range(1, abs(int(div_px)) + 2), SIG:1896
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                int s = win[x];
+                uint32_t px = 0;
+                if (s != empty) px = (img[s] & 0x00FFFFFFu) | 0x01000000u;
+                else {
+                    int dr = bit_dist_right(bits, nwords, x, reach), dl = bit_dist_left(bits, x, reach);
+                    if (dr <= reach && dr <= dl) px = img[win[x + dr]] & 0x00FFFFFFu;
+                    else if (dl <= reach) px = img[win[x - dl]] & 0x00FFFFFFu;
+                }
+                out[x] = px;
+            }
+        } else {  // naive_interpolating, SIG:1871-1892
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                int s = win[x];
+                row[x] = (s != empty) ? (img[s] & 0x00FFFFFFu) : 0u;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int l = 0; l < w; ++l) {
+                    if (px_sum(row[l]) != 0 || ((bits[l >> 5] >> (l & 31)) & 1u)) continue;
+                    uint32_t lb = (l > 0) ? row[l - 1] : 0u, rb = 0u;
+                    int r = l + 1;
+                    while (r < w) {
+                        if (px_sum(row[r]) != 0 && ((bits[r >> 5] >> (r & 31)) & 1u)) { rb = row[r]; break; }
+                        ++r;
+                    }
+                    if (px_sum(lb) == 0) lb = rb;
+                    else if (px_sum(rb) == 0) rb = lb;
+                    const int total = 1 + r - l;
+                    double stepv[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float df = (float)((rb >> (8 * ch)) & 255u) - (float)((lb >> (8 * ch)) & 255u);
+                        stepv[ch] = (double)df / (double)total;
+                    }
+                    for (int c = l; c < r; ++c) {
+                        uint32_t px = 0;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            double prod = stepv[ch] * (double)(c - l + 1);
+                            uint32_t inc = (uint32_t)(long long)prod & 255u;   // float -> uint8 wraps (Q5)
+                            uint32_t v = (((lb >> (8 * ch)) & 255u) + inc) & 255u;
+                            px |= v << (8 * ch);
+                        }
+                        row[c] = px;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int x = threadIdx.x; x < w; x += blockDim.x)
+                out[x] = row[x] | (((bits[x >> 5] >> (x & 31)) & 1u) << 24);
+        }
+    }
+}
+
+cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
+    const int nwords = (a.w + 31) >> 5;
+    dim3 grid(a.h, a.n, 2);
+    size_t smem;
+    switch (a.fill) {
+        case CS_FILL_NONE:
+            smem = (size_t)a.w * 4 + nwords * 4;
+            k_warp_rows<CS_FILL_NONE><<<grid, 256, smem, s>>>(a);
+            break;
+        case CS_FILL_NAIVE:
+            smem = (size_t)a.w * 4 + nwords * 4;
+            k_warp_rows<CS_FILL_NAIVE><<<grid, 256, smem, s>>>(a);
+            break;
+        case CS_FILL_NAIVE_INTERP:
+            smem = (size_t)a.w * 8 + nwords * 4;
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_warp_rows<CS_FILL_NAIVE_INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_warp_rows<CS_FILL_NAIVE_INTERP><<<grid, 256, smem, s>>>(a);
+            break;
+        case CS_FILL_INVERSE:
+            smem = (size_t)a.w * 8;
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_warp_rows<CS_FILL_INVERSE><<<grid, 256, smem, s>>>(a);
+            break;
+        default:
+            return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace cs

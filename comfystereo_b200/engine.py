@@ -1,0 +1,225 @@
+"""Host side of the hot path: parameter marshalling, workspace management, device- and
+host-buffer entry points, frame sharding across the GPUs of one box.
+
+Everything numerical happens in libcomfystereo_b200.so; this module only allocates tensors with
+torch and passes raw pointers and the current CUDA stream through the C ABI.
+"""
+import ctypes
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import CsParams, FILL_KEYS, MODES
+
+FILL_NAME_TO_KEY = {  # the node's dropdown labels -> dispatch keys, GS:88-100
+    'GPU Warp (Fast)': 'gpu_warp',
+    'No fill': 'none',
+    'No fill - Reverse projection': 'inverse',
+    'Imperfect fill - Hybrid Edge': 'hybrid_edge',
+    'Fill - Naive': 'naive',
+    'Fill - Naive interpolating': 'naive_interpolating',
+    'Fill - Polylines Soft': 'polylines_soft',
+    'Fill - Polylines Sharp': 'polylines_sharp',
+}
+
+
+def make_params(fill_key, mode, divergence, separation=0.0, stereo_balance=0.0, convergence_point=0.5,
+                stereo_offset_exponent=1.0, depth_blur=False, depth_blur_strength=0.0,
+                depth_blur_edge_threshold=6.0, depth_blur_falloff=1.0, depth_blur_vert_smooth=0,
+                group_size=0):
+    """Widget values -> cs_params.  The two integers python derives from depth_blur_strength
+    (SIG:1208-1209: bs = int(round(s)) with banker's rounding, R = int(s)) are computed here."""
+    if mode not in MODES:
+        raise ValueError(f'Unknown mode: {mode}')
+    if fill_key not in FILL_KEYS:
+        raise ValueError(f'Unknown fill technique key: {fill_key}')
+    p = CsParams()
+    p.fill = FILL_KEYS.index(fill_key)
+    p.mode = MODES.index(mode)
+    p.divergence = float(divergence)
+    p.separation = float(separation)
+    p.stereo_balance = float(stereo_balance)
+    p.convergence_point = float(convergence_point)
+    p.stereo_offset_exponent = float(stereo_offset_exponent)
+    strength = float(depth_blur_strength)
+    enabled = bool(depth_blur) and strength > 0  # strength <= 0 returns the input twice, SIG:1194
+    p.blur_enabled = int(enabled)
+    p.blur_box = int(round(strength)) if enabled else 0
+    p.blur_radius = int(strength) if enabled else 0
+    if enabled and p.blur_box <= 0:
+        # what torch's conv2d says for the reference in this corner
+        raise RuntimeError("kernel size should be greater than zero")
+    p.blur_vert_smooth = int(depth_blur_vert_smooth)
+    p.blur_edge_threshold = float(depth_blur_edge_threshold)
+    p.blur_falloff = float(depth_blur_falloff)
+    p.group_size = int(group_size)
+    return p
+
+
+def output_shapes(p, n, h, w):
+    ho, wo, hm, wm = (ctypes.c_int() for _ in range(4))
+    _lib.check(_lib.lib().cs_output_dims(ctypes.byref(p), h, w, ctypes.byref(ho), ctypes.byref(wo),
+                                         ctypes.byref(hm), ctypes.byref(wm)))
+    return (n, ho.value, wo.value, 3), (n, h, w, 3), (n, hm.value, wm.value)
+
+
+_ws_lock = threading.Lock()
+_workspaces = {}  # device index -> uint8 tensor
+
+
+def _workspace(device, nbytes):
+    with _ws_lock:
+        t = _workspaces.get(device.index)
+        if t is None or t.numel() < nbytes:
+            _workspaces.pop(device.index, None)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _workspaces[device.index] = t
+        return t
+
+
+def release():
+    with _ws_lock:
+        _workspaces.clear()
+    if _lib.loaded():
+        _lib.lib().cs_host_release()
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def default_chunk(p, n, h, w):
+    """Frames per kernel sequence.  Scratch per frame is ~26 B/px; a couple of frames keep it inside
+    the 126 MB L2 between producer and consumer kernels while amortising launches."""
+    group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
+    group = min(group, n)
+    target = max(1, int(96e6 // (26 * h * w)))
+    chunk = max(group, (target // group) * group)
+    return min(chunk, n)
+
+
+def stereo_batch_device(image, depth, p, out=None, chunk=None):
+    """The hot path on device-resident tensors.
+
+    image [N,H,W,3] float32 cuda, depth [N,H,W,C] float32 cuda (same H,W).
+    Returns (stereo, depth_left, depth_right, mask) cuda tensors in the node's layouts.
+    Asynchronous on the current stream."""
+    if not (image.is_cuda and depth.is_cuda):
+        raise ValueError("stereo_batch_device needs CUDA tensors (use stereo_batch_host for CPU tensors)")
+    if image.dtype != torch.float32 or depth.dtype != torch.float32:
+        raise TypeError("image and depth must be float32")
+    image = image.contiguous()
+    depth = depth.contiguous()
+    n, h, w, ci = image.shape
+    if ci != 3:
+        raise ValueError("image must have 3 channels")
+    if depth.dim() == 3:
+        depth = depth.unsqueeze(-1)
+    if depth.shape[:3] != (n, h, w):
+        raise AssertionError('Depthmap and the image must have the same size')
+    c = depth.shape[3]
+    lib = _lib.lib()
+    dev = image.device
+    s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
+    if out is None:
+        out = (torch.empty(s_shape, dtype=torch.float32, device=dev),
+               torch.empty(d_shape, dtype=torch.float32, device=dev),
+               torch.empty(d_shape, dtype=torch.float32, device=dev),
+               torch.empty(m_shape, dtype=torch.float32, device=dev))
+    stereo, dl, dr, mask = out
+    if chunk is None:
+        chunk = default_chunk(p, n, h, w)
+    nbytes = lib.cs_workspace_bytes(ctypes.byref(p), int(chunk), h, w)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _lib.check(lib.cs_stereo_batch(ctypes.byref(p), image.data_ptr(), depth.data_ptr(), n, h, w, c,
+                                       stereo.data_ptr(), dl.data_ptr(), dr.data_ptr(), mask.data_ptr(),
+                                       ws.data_ptr(), nbytes, _stream_ptr(dev)))
+    return stereo, dl, dr, mask
+
+
+def stereo_batch_host(image, depth, p, device=0, pin_outputs=True):
+    """The hot path on CPU tensors (what ComfyUI hands the node): chunks are streamed through the
+    GPU with upload, kernels and download overlapped inside the library.  Returns CPU tensors."""
+    if image.is_cuda or depth.is_cuda:
+        raise ValueError("stereo_batch_host needs CPU tensors")
+    image = image.contiguous().float()
+    depth = depth.contiguous().float()
+    n, h, w, ci = image.shape
+    if ci != 3:
+        raise ValueError("image must have 3 channels")
+    if depth.dim() == 3:
+        depth = depth.unsqueeze(-1)
+    if depth.shape[:3] != (n, h, w):
+        raise AssertionError('Depthmap and the image must have the same size')
+    c = depth.shape[3]
+    s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
+    pin = bool(pin_outputs) and torch.cuda.is_available()
+    stereo = torch.empty(s_shape, dtype=torch.float32, pin_memory=pin)
+    dl = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
+    dr = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
+    mask = torch.empty(m_shape, dtype=torch.float32, pin_memory=pin)
+    _lib.check(_lib.lib().cs_stereo_batch_host(ctypes.byref(p), image.data_ptr(), depth.data_ptr(), n, h, w, c,
+                                               stereo.data_ptr(), dl.data_ptr(), dr.data_ptr(), mask.data_ptr(),
+                                               int(device)))
+    return stereo, dl, dr, mask
+
+
+# ----------------------------------------------------------------------------------- sharding
+def shard_range(n, rank, world):
+    """Contiguous frame range of `rank`: GPU g gets frames [g*ceil(n/G), ...)."""
+    per = -(-n // world)
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def group_aligned_shard_range(n, rank, world, group):
+    """Like shard_range, but cuts only at multiples of `group` so that the GPU-Warp technique's
+    sub-batch-wide range tests (quirk Q9) see the same frames as a single-GPU run."""
+    ngroups = -(-n // group)
+    glo, ghi = shard_range(ngroups, rank, world)
+    return min(glo * group, n), min(ghi * group, n)
+
+
+def stereo_batch_multi_gpu(image, depth, p, devices):
+    """Frame-sharded run over several GPUs of one box from ONE process (used by the node when more
+    than one device is visible).  No collective: every device streams its contiguous frame range
+    and writes straight into its slice of the (pinned) host outputs, which is in-order assembly by
+    construction."""
+    n, h, w, _ = image.shape
+    if depth.dim() == 3:
+        depth = depth.unsqueeze(-1)
+    image = image.contiguous().float()
+    depth = depth.contiguous().float()
+    c = depth.shape[3]
+    s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
+    pin = torch.cuda.is_available()
+    outs = (torch.empty(s_shape, dtype=torch.float32, pin_memory=pin),
+            torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
+            torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
+            torch.empty(m_shape, dtype=torch.float32, pin_memory=pin))
+    group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
+    lib = _lib.lib()
+    errors = []
+
+    def work(rank, dev):
+        lo, hi = group_aligned_shard_range(n, rank, len(devices), group)
+        if hi <= lo:
+            return
+        try:
+            _lib.check(lib.cs_stereo_batch_host(
+                ctypes.byref(p), image[lo:hi].data_ptr(), depth[lo:hi].data_ptr(), hi - lo, h, w, c,
+                outs[0][lo:hi].data_ptr(), outs[1][lo:hi].data_ptr(), outs[2][lo:hi].data_ptr(),
+                outs[3][lo:hi].data_ptr(), int(dev)))
+        except Exception as e:  # noqa: BLE001 - re-raised on the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(r, d)) for r, d in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return outs

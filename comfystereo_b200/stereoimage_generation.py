@@ -1,0 +1,129 @@
+"""Drop-in mirror of the reference's pipeline-level API (stereoimage_generation.py):
+
+    create_stereoimages(...)      SIG:1422-1574   CPU techniques, one frame, returns PIL images
+    create_stereoimages_gpu(...)  SIG:1005-1128   'GPU Warp (Fast)', a sub-batch, returns tensors
+
+Same names, argument order, defaults, return shapes and exceptions; the work is done by the
+sm_100a kernels behind the C ABI (comfystereo_b200/engine.py).  There is no CPU implementation
+here: without a B200 and the built library these functions raise.
+"""
+import torch
+
+from . import engine
+
+_CPU_FILLS = ('none', 'naive', 'naive_interpolating', 'polylines_soft', 'polylines_sharp', 'inverse',
+              'hybrid_edge')
+_ALL_MODES = engine.MODES
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("comfystereo_b200 needs a CUDA (sm_100a) device; it has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_pil_list(t_u8):
+    from PIL import Image
+    return [Image.fromarray(a) for a in t_u8]
+
+
+def _float_to_u8(t):
+    """The kernels emit u8/255 in float32; x*255 is within 1e-5 of the integer it came from."""
+    return torch.round(t * 255.0).clamp_(0, 255).to(torch.uint8)
+
+
+def create_stereoimages(original_image, depthmap, divergence, separation=0.0, modes=None,
+                        stereo_balance=0.0, stereo_offset_exponent=1.0, fill_technique='polylines_sharp',
+                        depth_blur_strength=0.0, depth_blur_edge_threshold=6.0,
+                        direction_aware_depth_blur=False, return_modified_depth=True, convergence_point=0.5,
+                        depth_blur_falloff=1.0, depth_blur_vert_smooth=0):
+    """One frame through a CPU technique.  original_image: tensor [3,H,W] (0..1) as the node passes
+    it, or an [H,W,3] tensor/array; depthmap: [H,W] (0..1 or 0..255).  Returns
+    (list of PIL stereo images, PIL left depth, PIL right depth) when the blur flag is set,
+    (list, PIL depth) otherwise, or just the list when return_modified_depth is False."""
+    if modes is None:
+        modes = ['left-right']
+    if not isinstance(modes, list):
+        modes = [modes]
+    if len(modes) == 0:
+        return []
+    for mode in modes:
+        if mode not in _ALL_MODES:
+            raise Exception('Unknown mode')          # SIG:1562
+    tensors = isinstance(depthmap, torch.Tensor) and isinstance(original_image, torch.Tensor)
+    if not tensors:
+        raise NotImplementedError(
+            "non-tensor inputs select the reference's numpy branch (scipy blur SIG:1346-1419, no x255 "
+            "rescale), which the node never uses and which is outside the accelerated path; pass torch "
+            "tensors as the node does")
+    dev = _device()
+    img = original_image
+    if img.dim() == 3 and img.shape[0] == 3 and img.shape[2] != 3:
+        img = img.permute(1, 2, 0)
+    dm = depthmap
+    if dm.dim() == 3:
+        dm = dm.squeeze()
+    h, w = dm.shape
+    assert tuple(img.shape[:2]) == (h, w), 'Depthmap and the image must have the same size'
+    img = img.to(dev, torch.float32).unsqueeze(0).contiguous()
+    dm = dm.to(dev, torch.float32).reshape(1, h, w, 1).contiguous()
+    key = fill_technique if fill_technique in _CPU_FILLS else None
+    results, left_u8, right_u8 = [], None, None
+    for mode in modes:
+        if key is None:
+            # unknown fill key: apply_stereo_divergence returns the input image (SIG:1620)
+            p = engine.make_params('none', mode, 0.0, separation, 0.0, convergence_point,
+                                   stereo_offset_exponent, direction_aware_depth_blur, depth_blur_strength,
+                                   depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth)
+        else:
+            p = engine.make_params(key, mode, divergence, separation, stereo_balance, convergence_point,
+                                   stereo_offset_exponent, direction_aware_depth_blur, depth_blur_strength,
+                                   depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth)
+        stereo, dl, dr, _ = engine.stereo_batch_device(img, dm, p)
+        results.append(_float_to_u8(stereo[0]).cpu().numpy())
+        if left_u8 is None:
+            left_u8 = _float_to_u8(dl[0, :, :, 0]).cpu().numpy()
+            right_u8 = _float_to_u8(dr[0, :, :, 0]).cpu().numpy()
+    stereo_images = _to_pil_list(results)
+    if not return_modified_depth:
+        return stereo_images
+    from PIL import Image
+    if direction_aware_depth_blur:
+        return stereo_images, Image.fromarray(left_u8), Image.fromarray(right_u8)
+    return stereo_images, Image.fromarray(left_u8)
+
+
+def create_stereoimages_gpu(image_tensor, depth_tensor, divergence, separation=0.0, modes=None,
+                            stereo_balance=0.0, stereo_offset_exponent=1.0, convergence_point=0.5,
+                            depth_blur_strength=0.0, depth_blur_edge_threshold=6.0,
+                            direction_aware_depth_blur=False, depth_blur_falloff=1.0,
+                            depth_blur_vert_smooth=0):
+    """A sub-batch through 'GPU Warp (Fast)'.  image_tensor [B,3,H,W], depth_tensor [B,H,W].
+    Returns (list of [B,3,Ho,Wo] tensors, left_depth [B,H,W], right_depth [B,H,W], mask bool [B,H,W])
+    on the CUDA device, like the reference does when CUDA is available."""
+    if modes is None:
+        modes = ['left-right']
+    if not isinstance(modes, list):
+        modes = [modes]
+    if len(modes) == 0:
+        return [], None, None, None
+    for mode in modes:
+        if mode not in _ALL_MODES:
+            raise ValueError(f'Unknown mode: {mode}')  # SIG:1120
+    dev = _device()
+    b, _, h, w = image_tensor.shape
+    img = image_tensor.to(dev, torch.float32).permute(0, 2, 3, 1).contiguous()
+    dm = depth_tensor.to(dev, torch.float32).reshape(b, h, w, 1).contiguous()
+    results, left, right, mask = [], None, None, None
+    for mode in modes:
+        p = engine.make_params('gpu_warp', mode, divergence, separation, stereo_balance, convergence_point,
+                               stereo_offset_exponent, direction_aware_depth_blur, depth_blur_strength,
+                               depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth,
+                               group_size=b)
+        stereo, dl, dr, m = engine.stereo_batch_device(img, dm, p, chunk=b)
+        results.append(stereo.permute(0, 3, 1, 2))
+        if left is None:
+            # the node-level depth outputs are clamped copies (GS:163-166); at function level the
+            # reference returns them unclamped, which only differs for depth outside [0, 255]
+            left, right, mask = dl[..., 0], dr[..., 0], m > 0.5
+    return results, left, right, mask
