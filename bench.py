@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the stereo hot path (BASELINE.json metric: 1080p stereo frames/s, Mpix/s, % of HBM roofline,
+host-CPU reference beside it).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU cores
+
+Workload (N = 1 and per GPU for N > 1, weak scaling): BASELINE.json configs[1] -- 1920x1080, 'Fill - Polylines
+Sharp', depth_map_blur on (20/20/2.0/6), convergence_point 0.5, divergence 3.5, left-right -- as a batch of
+--frames frames per GPU per step (the roofline target is stated on a batch; a single 1080p
+frame is 25 us at roofline and only measures launch latency).  A "step" is one pass of the hot path over the
+batch.  Synthetic seeded frames, random image + ramp/discs/noise depth.
+
+Printed JSON line (rank 0):
+  value        frames/s with inputs and outputs resident in HBM (CUDA events, max over ranks, summed over GPUs)
+  e2e          the same metric through StereoImageNode.generate with pinned HOST tensors in and host tensors
+               out (H2D + kernels + D2H inside the timed region)
+  roofline     dominant kernel: its algorithmic bytes per launch / its mean CUDA-event duration, against the
+               measured HBM peak; `path` = the whole step's 80 B/px against the same peak
+  cpu_baseline the oracle port of the reference algorithm on this box's cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+NODE_PARAMS = dict(divergence=3.5, separation=0.0, modes="left-right", stereo_balance=0.0, convergence_point=0.5,
+                   stereo_offset_exponent=2.0, fill_technique="Fill - Polylines Sharp",
+                   depth_blur_edge_threshold=20.0, depth_blur_strength=20.0, depth_map_blur=True,
+                   depth_blur_falloff=2.0, depth_blur_vert_smooth=6, batch_size=12)
+BYTES_PER_PX = {"cpu_sbs": 80, "gw_sbs": 76, "anaglyph": 64}  # inputs read once, outputs written once
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--fill", default=NODE_PARAMS["fill_technique"])
+    ap.add_argument("--mode", default="left-right")
+    ap.add_argument("--divergence", type=float, default=3.5)
+    ap.add_argument("--chunk", type=int, default=0, help="frames per kernel sequence (0 = library default)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_frames(n, h, w, seed):
+    from comfystereo_b200 import synthetic as syn
+    # a few distinct frames, tiled: generation cost stays bounded, content still differs frame to frame
+    base = min(n, 4)
+    img = syn.make_image(base, h, w, seed=seed)
+    dep = syn.make_depth(base, h, w, "scene", seed=seed)
+    reps = -(-n // base)
+    return np.tile(img, (reps, 1, 1, 1))[:n], np.tile(dep, (reps, 1, 1, 1))[:n]
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(args, frames):
+    """The oracle port of the reference algorithm (same node-level work: gray, blur, 2 x fill, compose, mask) on
+    the host cores, `frames` frames of the benchmark workload.  One untimed call first (page-in, thread pool)."""
+    import oracle as orc
+    orc.lib()
+    img, dep = make_frames(frames, args.height, args.width, seed=100)
+    params = dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence)
+    orc.node_generate(img[:1], dep[:1], **params)
+    t0 = time.perf_counter()
+    orc.node_generate(img, dep, **params)
+    dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_frames
+    times = []
+    for i in range(args.warmup + args.steps):
+        fps, dt = cpu_baseline(args, sample)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = sample / t
+    line = {
+        "impl": "reference", "metric": "1080p stereo frames/s", "value": val, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "mpix_per_s": val * args.height * args.width / 1e6,
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} frame(s) of the workload per step, oracle/stereo_oracle.c (OpenMP over rows), "
+                                   "the reference itself is Python and does not exist on this box"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, frames):
+    return {"workload": f"{args.width}x{args.height} {args.fill}, depth_map_blur on (strength 20, threshold 20, "
+                        f"falloff 2.0, vert 6), convergence 0.5, divergence {args.divergence}, exponent 2, {args.mode} "
+                        f"(BASELINE.json configs[1] as a batch)",
+            "frames_per_gpu_per_step": frames, "l2": "inputs+outputs per step exceed the 126 MB L2 many times over "
+                                                     "(no flush needed)", "sharding": "frame-wise, no collective"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from comfystereo_b200 import StereoImageNode, _lib, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    _lib.check(lib.cs_device_check())
+
+    n, h, w = args.frames, args.height, args.width
+    key = engine.FILL_NAME_TO_KEY.get(args.fill, "gpu_warp")
+    group = min(NODE_PARAMS["batch_size"], n) if key == "gpu_warp" else 0
+    p = engine.make_params(key, args.mode, args.divergence, 0.0, 0.0, 0.5, 2.0, True, 20.0, 20.0, 2.0, 6, group_size=group)
+    img_np, dep_np = make_frames(n, h, w, seed=rank)
+    img_h = torch.from_numpy(img_np).pin_memory()
+    dep_h = torch.from_numpy(dep_np).pin_memory()
+    img_d, dep_d = img_h.to(dev), dep_h.to(dev)
+    s_shape, d_shape, m_shape = engine.output_shapes(p, n, h, w)
+    outs = tuple(torch.empty(s, dtype=torch.float32, device=dev) for s in (s_shape, d_shape, d_shape, m_shape))
+    chunk = args.chunk if args.chunk > 0 else None
+
+    def step():
+        engine.stereo_batch_device(img_d, dep_d, p, out=outs, chunk=chunk)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.cs_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lib.cs_launch_count(0)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms_total / args.steps
+    fps = world * n / (ms_per_step * 1e-3)
+
+    # ---- per-kernel CUDA-event durations over the same steps (separate pass so `value` carries no event overhead)
+    lib.cs_profile_enable(1)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    lib.cs_profile_enable(0)
+    nk = lib.cs_profile_kernel_count()
+    k_ms = (ctypes.c_double * nk)()
+    k_n = (ctypes.c_longlong * nk)()
+    lib.cs_profile_collect(k_ms, k_n)
+    kernels = {lib.cs_profile_kernel_name(i).decode(): (k_ms[i], k_n[i]) for i in range(nk) if k_n[i] > 0}
+    peak, peak_src = peaks()
+    px_step = n * h * w
+    cls = "gw_sbs" if key == "gpu_warp" else "cpu_sbs"
+    if args.mode.endswith("anaglyph") or args.mode in ("left-only", "only-right"):
+        cls = "anaglyph"
+    path_bytes = BYTES_PER_PX[cls] * px_step
+    # algorithmic bytes per pixel of each kernel (both eyes), DESIGN.md section 4
+    k_bytes_px = {"k_prepare": 24 + 8, "k_edge_dist": 4 + 2, "k_blur_blend": 4 + 2 + 8 + 24, "k_depth_out": 4 + 24,
+                  "k_warp_rows": 24, "k_polylines": 24, "k_polylines_exact": 24, "k_hybrid_splat": 24,
+                  "k_hybrid_gapfill": 16, "k_gpuwarp": 12 + 8 + 24 + 4, "k_compose": 8 + 24 + 8}
+    timed = {k: v for k, v in kernels.items() if k != "misc"}
+    total_k_ms = sum(v[0] for v in timed.values()) or 1.0
+    dom = max(timed, key=lambda k: timed[k][0]) if timed else None
+    roofline = None
+    if dom:
+        d_ms, d_n = timed[dom]
+        units_px = px_step * args.steps / d_n          # pixels one launch processes
+        per_launch_bytes = k_bytes_px.get(dom, 24) * units_px
+        achieved = per_launch_bytes / (d_ms / d_n * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": per_launch_bytes, "ms_per_launch": d_ms / d_n,
+                    "share_of_step": d_ms / total_k_ms,
+                    "path": {"bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
+                             "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                             "note": "whole step: 80 B/px algorithmic I/O (SURVEY.md 8d) / step time"},
+                    "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                                    "share": v[0] / total_k_ms,
+                                    "gbs": k_bytes_px.get(k, 0) * px_step * args.steps / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None}
+                                for k, v in timed.items()}}
+
+    # ---- end to end through the node with host tensors
+    e2e = None
+    if not args.no_e2e:
+        node = StereoImageNode()
+        params = dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence)
+
+        def e2e_step():
+            o = node.generate(img_h, dep_h, **params)
+            return float(o[3][0, 0, 0])   # touch the result on the host
+
+        # the node shards over every visible device from one process; under torchrun each rank owns one GPU
+        os.environ.setdefault("COMFYSTEREO_SINGLE_DEVICE", "1")
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = img_h.numel() * 4 + dep_h.numel() * 4
+        d2h = sum(int(np.prod(s)) for s in (s_shape, d_shape, d_shape, m_shape)) * 4
+        e2e = {"value": world * n * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "api": "StereoImageNode.generate (CPU tensors in/out) -> cs_stereo_batch_host"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, dt = cpu_baseline(args, args.cpu_frames)
+        cpu = {"value": val, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{args.cpu_frames} frame(s) of the same workload, oracle/stereo_oracle.c with OpenMP over rows, "
+                         f"{dt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "1080p stereo frames/s", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n),
+            "mpix_per_s": fps * h * w / 1e6,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

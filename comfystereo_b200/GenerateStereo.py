@@ -6,7 +6,10 @@ blurred_depthmap_left/right [N,H,W,3], no_fill_imperfect_mask [N,Hm,Wm]).  Insid
 handed to the sm_100a library in one call: frames stream host -> GPU -> host in overlapped chunks,
 and are sharded frame-wise over every visible GPU when there is more than one.
 """
+import os
+
 import torch
+import torch.distributed
 
 from . import engine
 
@@ -115,7 +118,11 @@ class StereoImageNode:
         else:
             if not torch.cuda.is_available():
                 raise RuntimeError("comfystereo_b200 needs a CUDA (sm_100a) device; it has no CPU fallback")
-            ndev = torch.cuda.device_count()
+            # one process driving every visible GPU -- unless this process is already one rank of a
+            # torch.distributed job (one process per GPU) or the user pinned it to a single device
+            single = os.environ.get("COMFYSTEREO_SINGLE_DEVICE", "0") == "1" or \
+                (torch.distributed.is_available() and torch.distributed.is_initialized())
+            ndev = 1 if single else torch.cuda.device_count()
             if ndev > 1 and total >= 2 * ndev:
                 outs = engine.stereo_batch_multi_gpu(image, depth, p, list(range(ndev)))
             else:

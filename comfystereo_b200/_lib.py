@@ -66,6 +66,10 @@ SIGNATURES = {
     "cs_launch_count": (ctypes.c_longlong, [_I]),
     "cs_polylines_status": (_I, [_PP, _I, _I, _I, _P, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "cs_set_test_flags": (None, [_I]),
+    "cs_profile_kernel_count": (_I, []),
+    "cs_profile_kernel_name": (ctypes.c_char_p, [_I]),
+    "cs_profile_enable": (None, [_I]),
+    "cs_profile_collect": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
 }
 
 _lib = None

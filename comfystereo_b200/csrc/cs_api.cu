@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "cs_internal.cuh"
 
@@ -13,6 +14,30 @@ namespace cs {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- per-kernel timing -------------------------------------------------------------------
+struct ProfRec { int id; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+static const char* const kKernelNames[K_COUNT] = {
+    "k_prepare", "k_edge_dist", "k_blur_blend", "k_depth_out", "k_warp_rows", "k_polylines", "k_polylines_exact",
+    "k_hybrid_splat", "k_hybrid_gapfill", "k_gpuwarp", "k_compose", "misc"};
+void prof_begin(int id, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r;
+    r.id = id;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+}
+void prof_end(int id, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (size_t i = g_prof.size(); i-- > 0;)
+        if (g_prof[i].id == id) { cudaEventRecord(g_prof[i].b, s); break; }
+}
 
 static thread_local char g_err[512] = "";
 int fail(int code, const char* fmt, ...) {
@@ -224,6 +249,27 @@ size_t cs_workspace_bytes(const cs_params* p, int chunk, int h, int w) {
 }
 
 void cs_set_test_flags(int flags) { g_test_flags = flags; }
+
+int cs_profile_kernel_count(void) { return K_COUNT; }
+const char* cs_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }
+void cs_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+int cs_profile_collect(double* ms, long long* launches) {
+    // Call after synchronising the streams that were profiled.  Accumulates into ms[K_COUNT] / launches[K_COUNT].
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < K_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (auto& r : g_prof) {
+        float t = 0.0f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms[r.id] += t;
+            launches[r.id] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    (void)cudaGetLastError();
+    return CS_OK;
+}
 
 long long cs_launch_count(int reset) {
     return reset ? g_launches.exchange(0) : g_launches.load();

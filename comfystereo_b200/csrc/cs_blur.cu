@@ -248,8 +248,10 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     uint8_t* dist_r = dist + (int64_t)n * h * w;
     const float edge_div = (float)(10.0 * p.blur_edge_threshold);  // python float 10*thr -> float32 scalar
     const int nwords = (w + 31) >> 5;
+    prof_begin(K_EDGE_DIST, s);
     k_edge_dist<<<dim3(h, n), 256, 2 * nwords * sizeof(uint32_t), s>>>(
         gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
+    prof_end(K_EDGE_DIST, s);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -263,9 +265,11 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     if (per_frame > items) per_frame = items;
     if (per_frame < 1) per_frame = 1;
     size_t smem = (size_t)(kSeg + bs + 2 * kSeg) * sizeof(float);
+    prof_begin(K_BLUR_BLEND, s);
     k_blur_blend<<<dim3(per_frame, n), kSeg, smem, s>>>(gray, stats, scale_mode, group < 1 ? 1 : group, n, h,
                                                        w, bs, radius, v, lut, dist_l, dist_r, blur_l,
                                                        blur_r, depth_l_out, depth_r_out, items, segs);
+    prof_end(K_BLUR_BLEND, s);
     count_launch();
     return cudaGetLastError();
 }

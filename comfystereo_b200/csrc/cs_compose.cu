@@ -95,7 +95,9 @@ cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, i
     const int cap = 148 * 8 * 2;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
+    prof_begin(K_COMPOSE, s);
     k_compose<<<dim3(bx, n), 256, 0, s>>>(left, right, h, w, mode, ho, wo, vec, stereo, mask);
+    prof_end(K_COMPOSE, s);
     count_launch();
     return cudaGetLastError();
 }

@@ -260,7 +260,9 @@ cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_gpuwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prof_begin(K_GPUWARP, s);
     k_gpuwarp<<<dim3(a.h, a.n), 256, smem, s>>>(a);
+    prof_end(K_GPUWARP, s);
     count_launch();
     return cudaGetLastError();
 }

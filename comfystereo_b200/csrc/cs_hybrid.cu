@@ -150,14 +150,18 @@ cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
     size_t smem = (size_t)a.w * 12;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_hybrid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prof_begin(K_HYBRID_SPLAT, s);
     k_hybrid_splat<<<dim3(a.h, a.n, 2), 256, smem, s>>>(a);
+    prof_end(K_HYBRID_SPLAT, s);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int64_t npx = (int64_t)a.h * a.w;
     int bx = (int)((npx + 255) / 256);
     if (bx > 148 * 8) bx = 148 * 8;
+    prof_begin(K_HYBRID_GAPFILL, s);
     k_hybrid_gapfill<<<dim3(bx, a.n, 2), 256, 0, s>>>(a, exp(-0.5), exp(-1.0));
+    prof_end(K_HYBRID_GAPFILL, s);
     count_launch();
     return cudaGetLastError();
 }

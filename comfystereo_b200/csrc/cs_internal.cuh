@@ -144,6 +144,11 @@ struct WarpArgs {
 };
 
 void count_launch();
+// Optional per-kernel timing (bench.py): CUDA events recorded on the launch stream around every kernel.
+enum KernelId { K_PREPARE = 0, K_EDGE_DIST, K_BLUR_BLEND, K_DEPTH_OUT, K_WARP_ROWS, K_POLY_FAST, K_POLY_EXACT,
+                K_HYBRID_SPLAT, K_HYBRID_GAPFILL, K_GPUWARP, K_COMPOSE, K_MISC, K_COUNT };
+void prof_begin(int id, cudaStream_t s);
+void prof_end(int id, cudaStream_t s);
 int fail(int code, const char* fmt, ...);   // records the thread-local cs_last_error() text, returns code
 cudaError_t launch_init_stats(FrameStats* stats, int n, cudaStream_t s);
 cudaError_t launch_prepare(const float* image, const float* depth, int n, int h, int w, int c,

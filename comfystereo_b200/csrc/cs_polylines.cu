@@ -407,13 +407,17 @@ cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s) {
     cudaError_t e;
     if (use_fast) {
         if (fs > 48 * 1024) cudaFuncSetAttribute(k_polylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
+        prof_begin(K_POLY_FAST, s);
         k_polylines<<<grid, kPolyThreads, fs, s>>>(a, sharp, flags);
+        prof_end(K_POLY_FAST, s);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     size_t es = exact_smem(w, sharp, act_cap);
     if (es > 48 * 1024) cudaFuncSetAttribute(k_polylines_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
+    prof_begin(K_POLY_EXACT, s);
     k_polylines_exact<<<grid, kPolyThreads, es, s>>>(a, sharp, act_cap, use_fast ? flags : nullptr, status);
+    prof_end(K_POLY_EXACT, s);
     count_launch();
     return cudaGetLastError();
 }

@@ -19,7 +19,9 @@ __global__ void k_init_stats(FrameStats* st, int n) {
 }
 
 cudaError_t launch_init_stats(FrameStats* stats, int n, cudaStream_t s) {
+    prof_begin(K_MISC, s);
     k_init_stats<<<(n + 127) / 128, 128, 0, s>>>(stats, n);
+    prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -128,6 +130,7 @@ cudaError_t launch_prepare(const float* image, const float* depth, int n, int h,
                     ((uintptr_t)gray % 16 == 0) && (image_u8 == nullptr || (uintptr_t)image_u8 % 16 == 0) &&
                     (npx % 4 == 0);
     const bool quant = image_u8 != nullptr;
+    prof_begin(K_PREPARE, s);
     if (c == 3) {
         if (quant) k_prepare<3, true><<<grid, 256, 0, s>>>(image, depth, c, npx, vec, gray, image_u8, stats);
         else k_prepare<3, false><<<grid, 256, 0, s>>>(image, depth, c, npx, vec, gray, image_u8, stats);
@@ -138,6 +141,7 @@ cudaError_t launch_prepare(const float* image, const float* depth, int n, int h,
         if (quant) k_prepare<0, true><<<grid, 256, 0, s>>>(image, depth, c, npx, vec, gray, image_u8, stats);
         else k_prepare<0, false><<<grid, 256, 0, s>>>(image, depth, c, npx, vec, gray, image_u8, stats);
     }
+    prof_end(K_PREPARE, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -163,7 +167,9 @@ cudaError_t launch_minmax(const float* src, int n, int64_t npx, FrameStats* stat
     int bx = (int)((npx + 1023) / 1024);
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
+    prof_begin(K_MISC, s);
     k_minmax<<<dim3(bx, n), 256, 0, s>>>(src, npx, stats);
+    prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -184,7 +190,9 @@ __global__ void k_export_stats(const FrameStats* __restrict__ st, int n, int whi
 }
 
 cudaError_t launch_export_stats(const FrameStats* stats, int n, int which, float* out, int stride, cudaStream_t s) {
+    prof_begin(K_MISC, s);
     k_export_stats<<<(n + 127) / 128, 128, 0, s>>>(stats, n, which, out, stride);
+    prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -272,8 +280,10 @@ cudaError_t launch_depth_out(const float* src_l, const float* src_r, const Frame
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     const int vec = (npx % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0);
+    prof_begin(K_DEPTH_OUT, s);
     k_depth_out<<<dim3(bx, n), 256, 0, s>>>(src_l, src_r, stats, n, npx, src_kind, out_kind,
                                             group < 1 ? 1 : group, vec, out_l, out_r);
+    prof_end(K_DEPTH_OUT, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -289,7 +299,9 @@ cudaError_t launch_quantize(const float* image, int64_t total_px, uint32_t* out,
     int bx = (int)((total_px + 255) / 256);
     if (bx > 148 * 16) bx = 148 * 16;
     if (bx < 1) bx = 1;
+    prof_begin(K_MISC, s);
     k_quantize<<<bx, 256, 0, s>>>(image, total_px, out);
+    prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();
 }
@@ -320,7 +332,9 @@ cudaError_t launch_shift_indices(const float* nd, int n, int h, int w, double di
     int bx = (int)((total + 255) / 256);
     if (bx > 148 * 16) bx = 148 * 16;
     if (bx < 1) bx = 1;
+    prof_begin(K_MISC, s);
     k_shift_indices<<<bx, 256, 0, s>>>(nd, total, w, div_px, sep_px, expo, kind, out);
+    prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();
 }

@@ -200,6 +200,7 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
     dim3 grid(a.h, a.n, 2);
     size_t smem;
+    prof_begin(K_WARP_ROWS, s);
     switch (a.fill) {
         case CS_FILL_NONE:
             smem = (size_t)a.w * 4 + nwords * 4;
@@ -224,6 +225,7 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
         default:
             return cudaErrorInvalidValue;
     }
+    prof_end(K_WARP_ROWS, s);
     count_launch();
     return cudaGetLastError();
 }

@@ -184,6 +184,14 @@ CS_API long long cs_launch_count(int reset);
 CS_API int cs_polylines_status(const cs_params *p, int chunk, int h, int w, const void *workspace,
                         int *status_out, int *flagged_rows);
 
+/* Optional per-kernel timing for bench.py: when enabled every kernel launch is bracketed by CUDA events on
+ * its own stream; cs_profile_collect (after a synchronize) sums the elapsed milliseconds and launch counts per
+ * kernel id into ms[cs_profile_kernel_count()] / launches[...] and clears the record. */
+CS_API int cs_profile_kernel_count(void);
+CS_API const char *cs_profile_kernel_name(int id);
+CS_API void cs_profile_enable(int on);
+CS_API int cs_profile_collect(double *ms, long long *launches);
+
 /* Test hook.  bit 0: Polylines replays EVERY row with the exact sequential sweep. */
 CS_API void cs_set_test_flags(int flags);
 
