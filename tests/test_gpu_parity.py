@@ -138,21 +138,29 @@ def test_node_vs_oracle_and_reference(gu, oracle, node, spec):
     o_st, o_dl, o_dr, o_mk = oracle.node_generate(img, dep, **params)
     fill = params["fill_technique"]
     blur_on = "blur_l" in g.files
-    # on few-level ('quant') depth every z-test / closeness comparison between equal levels is decided by the
-    # float32 ulp noise of the blur, so more pixels follow the reference's conv2d rounding than elsewhere
-    lim = 5e-2 if spec["kind"] == "quant" else 5e-3
+    # Depth with exact plateaus (flat / steps / card / quant) + blur: inside a plateau the blurred value is
+    # "the plateau +- float32 summation noise", and min/max normalisation or a z-test between equal levels turns
+    # that noise into whole-pixel decisions.  Those pixels follow the rounding of whichever conv2d produced the
+    # blur, so the end-to-end comparison with the reference's fixture is only meaningful on continuous depth;
+    # plateau classes are held to the bar stage-wise, with the reference's own blurred depth injected
+    # (test_stagewise_with_reference_blur / test_forward_warp_with_reference_blur).
+    chaotic = blur_on and spec["kind"] in ("flat", "steps", "card", "quant")
+    lim = 5e-3
     assert stereo.shape == o_st.shape and dl.shape == o_dl.shape and mask.shape == o_mk.shape
     assert stereo.dtype == np.float32 and mask.dtype == np.float32
     if fill == 'GPU Warp (Fast)':
         # (a) oracle: same blur order -> identical depth, identical mask, image to float32 rounding
         assert np.array_equal(dl, o_dl) and np.array_equal(dr, o_dr)
         assert np.array_equal(mask, o_mk)
-        assert np.abs(stereo - o_st).max() <= 1e-6
+        special = params["stereo_offset_exponent"] in (1.0, 2.0, 0.5, 3.0)   # otherwise powf: CUDA vs libm, 1 ulp
+        assert np.abs(stereo - o_st).max() <= (1e-6 if special else 1e-5)
         # (b) reference
         assert np.abs(dl[..., 0] - g["depth_l"]).max() <= 1e-6 and np.abs(dr[..., 0] - g["depth_r"]).max() <= 1e-6
         bad_mask = ((mask > 0).astype(np.uint8) != g["mask"]).mean()
         bad_px = (np.abs(stereo - g["stereo"]).max(axis=-1) > 1.0 / 255).mean()
-        if blur_on:
+        if chaotic:
+            pass
+        elif blur_on:
             assert bad_mask <= lim and bad_px <= lim, (bad_mask, bad_px)
         else:
             assert bad_mask == 0 and np.abs(stereo - g["stereo"]).max() <= 2e-5
@@ -170,13 +178,21 @@ def test_node_vs_oracle_and_reference(gu, oracle, node, spec):
         assert circ_dist_u8(q(dr[..., 0]), g["depth_r"]).max() <= 1
         bad_px = (np.abs(q(stereo).astype(np.int32) - g["stereo"].astype(np.int32)).max(axis=-1) > 1).mean()
         bad_mask = (q(mask) != g["mask"]).mean()
-        if blur_on:
+        if chaotic:
+            pass
+        elif blur_on:
             assert bad_px <= lim and bad_mask <= lim, (bad_px, bad_mask)
         else:
             assert bad_px == 0 and bad_mask == 0, (bad_px, bad_mask)
 
 
-@pytest.mark.parametrize("name", ["scene_6", "cfg2_polysharp", "quant_PolylinesSharp", "scene_2", "scene_4"])
+_BLUR_CPU = [s["name"] for s in MAN["node"] if s["params"]["depth_map_blur"]
+             and s["params"]["fill_technique"] != 'GPU Warp (Fast)']
+_BLUR_GW = [s["name"] for s in MAN["node"] if s["params"]["depth_map_blur"]
+            and s["params"]["fill_technique"] == 'GPU Warp (Fast)']
+
+
+@pytest.mark.parametrize("name", _BLUR_CPU)
 def test_stagewise_with_reference_blur(gu, oracle, name):
     """SURVEY section 8 parity protocol, step 1: feed the REFERENCE's captured blurred depth to the warp stage
     and require the integer-exact bar against the oracle (which test_oracle_golden pins to the reference
@@ -188,19 +204,68 @@ def test_stagewise_with_reference_blur(gu, oracle, name):
     key = oracle.FILL_NAME_TO_KEY[p["fill_technique"]]
     w = spec["w"]
     img_u8 = np.clip(img * np.float32(255), 0, 255).astype(np.uint8)
+    stereo_g = g["stereo"]
+    mode = p["modes"]
     for eye, (blur, sign) in enumerate(((g["blur_l"], +1), (g["blur_r"], -1))):
         div = sign * p["divergence"] * (1 + sign * p["stereo_balance"])
         sep = -sign * p["separation"]
+        if abs(div) < 0.001:
+            continue  # passthrough eye (SIG:1536)
         got = gu.warp_fill(img_u8, blur, key, div, sep, p["stereo_offset_exponent"], p["convergence_point"])[..., :3]
         for f in range(spec["n"]):
             want = oracle.apply_stereo_divergence(img_u8[f], blur[f], div, sep, p["stereo_offset_exponent"], key,
                                                   p["convergence_point"])
             d = np.abs(got[f].astype(np.int32) - want.astype(np.int32))
             assert d.max() <= (1 if key == 'hybrid_edge' else 0), (eye, f, d.max(), (d > 0).sum())
-            # the reference's composed output holds this eye in its left / right half
-            half = g["stereo"][f][:, :w] if eye == 0 else g["stereo"][f][:, w:]
-            if key != 'hybrid_edge':
+            # the reference's composed output holds this eye in one of its halves
+            first = (eye == 0) == (mode in ("left-right", "top-bottom"))
+            if mode in ("left-right", "right-left"):
+                half = stereo_g[f][:, :w] if first else stereo_g[f][:, w:]
+            elif mode in ("top-bottom", "bottom-top"):
+                half = stereo_g[f][:spec["h"]] if first else stereo_g[f][spec["h"]:]
+            else:
+                half = None  # anaglyph mixes channels of both eyes; covered by the oracle comparison above
+            if key != 'hybrid_edge' and half is not None:
                 assert np.array_equal(got[f], half)
+
+
+@pytest.mark.parametrize("name", _BLUR_GW)
+def test_forward_warp_with_reference_blur(gu, name):
+    """Same protocol for 'GPU Warp (Fast)': forward_warp_gpu on the reference's captured blurred depth must
+    reproduce the reference's mask bit for bit and its float image to 2e-5."""
+    spec = next(s for s in MAN["node"] if s["name"] == name)
+    g = load_golden("node", name)
+    img, _ = _node_inputs(spec)
+    p = spec["params"]
+    n, h, w = spec["n"], spec["h"], spec["w"]
+    gb = min(p["batch_size"], n)
+    mode = p["modes"]
+    masks = []
+    for eye, (blur, sign) in enumerate(((g["blur_l"], +1), (g["blur_r"], -1))):
+        div = p["divergence"] * (1 + sign * p["stereo_balance"])
+        if div < 0.001:
+            masks.append(np.zeros((n, h, w), bool))
+            continue
+        div_px = sign * (div / 100.0) * w
+        sep_px = -sign * (p["separation"] / 100.0) * w
+        outs, mks = [], []
+        for s0 in range(0, n, gb):   # the "/255 if any frame max > 1" test is sub-batch wide (Q9)
+            o, m = gu.forward_warp(img[s0:s0 + gb], blur[s0:s0 + gb], div_px, sep_px, p["stereo_offset_exponent"],
+                                   p["convergence_point"])
+            outs.append(o)
+            mks.append(m)
+        got = np.concatenate(outs)
+        masks.append(np.concatenate(mks))
+        first = (eye == 0) == (mode in ("left-right", "top-bottom"))
+        if mode in ("left-right", "right-left"):
+            want = g["stereo"][:, :, :w] if first else g["stereo"][:, :, w:]
+        elif mode in ("top-bottom", "bottom-top"):
+            want = g["stereo"][:, :h] if first else g["stereo"][:, h:]
+        else:  # red-cyan: R from the left eye, G and B from the right eye
+            ch = slice(0, 1) if eye == 0 else slice(1, 3)
+            got, want = got[..., ch], g["stereo"][..., ch]
+        assert np.abs(got - want).max() <= 2e-5
+    assert np.array_equal((masks[0] | masks[1]).astype(np.uint8), g["mask"])
 
 
 def test_device_path_equals_host_path(gu, node):
