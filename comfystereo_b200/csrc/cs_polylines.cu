@@ -261,115 +261,481 @@ __global__ void __launch_bounds__(kPolyThreads) k_polylines_exact(const WarpArgs
 }
 
 // ------------------------------------------------------------------------------------------
-// fast sweep: thread per output column, set-based selection, flags order-dependent rows
+// fast sweep
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPolyThreads) k_polylines(const WarpArgs a, int sharp, int* __restrict__ row_flags) {
+// Conversions between float32 and float64 (F2F / I2F) issue on the 16-lane XU pipe and were the
+// bottleneck of the first version of this kernel (ncu: xu pipe saturated, fp64 pipe 12 % busy).
+// The hot loop therefore never converts: float32 values are widened and float64 sums are rounded
+// to float32 precision with integer bit operations on the ALU pipe, which is exact.
+
+// exact float32 -> float64 for normal numbers (zero / denormal / inf / nan take the hardware path)
+__device__ __forceinline__ double widen(float f) {
+    uint32_t b = __float_as_uint(f);
+    uint32_t e = (b >> 23) & 0xFFu;
+    if (e == 0u || e == 255u) return (double)f;
+    uint32_t hi = (b & 0x80000000u) | (((b >> 3) & 0x0FFFFFFFu) + 0x38000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
+// round-to-nearest-even of a float64 to 24 significant bits, result kept as float64.
+// Equals (double)(float)x whenever (float)x is a normal float32.
+__device__ __forceinline__ double round24(double x) {
+    uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+    uint32_t nlo = lo + 0x0FFFFFFFu + ((lo >> 29) & 1u);
+    hi += (nlo < lo) ? 1u : 0u;
+    return __hiloint2double((int)hi, (int)(nlo & 0xE0000000u));
+}
+// float64 -> float32, round to nearest even, without F2F when the result is a normal float32
+__device__ __forceinline__ float narrow(double x) {
+    uint32_t e = ((uint32_t)__double2hiint(x) >> 20) & 0x7FFu;
+    if (e <= 897u || e >= 1150u) return (float)x;
+    double r = round24(x);
+    uint32_t hi = (uint32_t)__double2hiint(r), lo = (uint32_t)__double2loint(r);
+    return __uint_as_float((hi & 0x80000000u) | (((hi & 0x7FFFFFFFu) - 0x38000000u) << 3) | (lo >> 29));
+}
+// uint8 -> float64 without I2F: 2^52 + v is exact, subtracting 2^52 leaves v
+__device__ __forceinline__ double u8_to_f64(uint32_t v) {
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+struct PolyCtx {
+    const float* px;        // [npts] source-order x (float32)
+    const double* sxd;      // [npts] sorted x, widened
+    const uint32_t* info;   // [npts] sorted -> source point index (low 16 bits) | kSimple
+    const float* reach;     // [npts] prefix max (sorted order) of segment ends
+    const float* clo;       // [w]
+    const int* start;       // [w+3] first sorted rank of bucket b = floor(x)+1
+    RowCtx row;
+};
+constexpr uint32_t kSimple = 0x10000u;
+
+__device__ __forceinline__ double visit_ctr(const PolyCtx& c, int col, int k, double* sig_out) {
+    double pa = c.sxd[k], pb = c.sxd[k + 1];
+    double from = fmax((double)col, pa) + kEps;
+    double to = fmin((double)(col + 1), pb) - kEps;
+    double sig = to - from;
+    *sig_out = sig;
+    return from + 0.5 * sig;
+}
+
+// number of active segments at ctr (interval k); *which = sorted index of the last one found
+__device__ __forceinline__ int active_count(const PolyCtx& c, int k, double ctr, int* which) {
+    int n = 0;
+    for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
+        int sp = (int)(c.info[j] & 0xFFFFu);
+        if (!(c.sxd[j] < ctr) || ((double)c.px[sp + 1] < ctr)) continue;
+        ++n;
+        *which = j;
+    }
+    return n;
+}
+
+// The reference's selection when the result depends on the ORDER of its active list (quirk Q7):
+// find the nearest earlier visit with exactly one active segment (there the list is [that segment],
+// whatever happened before), replay the append / swap-remove list from there to the target visit,
+// then choose as the reference does.  Returns the source point index of the chosen segment, or -1
+// when the replay does not fit its budget (the whole row is then redone sequentially).
+__device__ __noinline__ int replay_choice(const PolyCtx& c, int col, int k) {
+    constexpr int kCap = 64, kBudget = 6000;
+    unsigned short lst[kCap];
+    const int nsg = c.row.nsg;
+    // ---- backward: locate the reset visit
+    int rc = col, rk = k, sgp = 0, steps = 0;
+    bool from_row_start = false;
+    while (true) {
+        // previous visit
+        if (rk > c.start[rc + 1] - 1) --rk;
+        else if (rc > 0) { --rc; rk = c.start[rc + 2] - 1; }
+        else { from_row_start = true; break; }
+        if (++steps > kBudget) return -1;
+        double sig;
+        double ctr = visit_ctr(c, rc, rk, &sig);
+        int which = 0;
+        if (active_count(c, rk, ctr, &which) == 1) { sgp = which; break; }
+    }
+    int n = 0;
+    if (from_row_start) { rc = 0; rk = c.start[1] - 1; sgp = 0; }
+    // ---- forward: replay list maintenance up to and including the target visit
+    while (true) {
+        double sig;
+        double ctr = visit_ctr(c, rc, rk, &sig);
+        while (sgp < nsg && c.sxd[sgp] < ctr) {
+            if (n >= kCap) return -1;
+            lst[n++] = (unsigned short)(c.info[sgp] & 0xFFFFu);
+            ++sgp;
+        }
+        for (int i = 0; i < n;) {
+            if ((double)c.px[lst[i] + 1] < ctr) { lst[i] = lst[n - 1]; --n; }
+            else ++i;
+        }
+        if (rc == col && rk == k) {
+            if (n == 0) return -1;
+            int best = 0;
+            if (n != 1) {
+                double bestc = -kEps;
+                for (int i = 0; i < n; ++i) {
+                    int sp = lst[i];
+                    float x0 = c.px[sp], x1 = c.px[sp + 1];
+                    float den = x1 - x0;
+                    double ip = (ctr - (double)x0) / (double)den;
+                    double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+                    double cl = t0 + t1;
+                    if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
+                }
+            }
+            return lst[best];
+        }
+        // next visit
+        if (rk < c.start[rc + 2] - 1) ++rk;
+        else { ++rc; rk = c.start[rc + 1] - 1; }
+    }
+}
+
+// Any visit that is not "exactly one active segment, the one starting at the interval's left point":
+// builds the active set, selects in FP64 like the reference, and resolves order-dependent choices by replay.
+// Returns the source point index of the chosen segment (-1: nothing active), -2: give up (row flagged).
+__device__ __noinline__ int general_visit(const PolyCtx& c, int col, int k, double ctr) {
+    int nact = 0, best = -1, only = -1, nbest = 0;
+    double bestc = -kEps;
+    for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
+        int sp = (int)(c.info[j] & 0xFFFFu);
+        float x0 = c.px[sp], x1 = c.px[sp + 1];
+        if (!((double)x0 < ctr) || ((double)x1 < ctr)) continue;
+        ++nact;
+        only = sp;
+        float den = x1 - x0;
+        double ip = (ctr - (double)x0) / (double)den;
+        double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+        double cl = t0 + t1;
+        if (0.0 < ip && ip < 1.0) {
+            if (bestc < cl) { bestc = cl; best = sp; nbest = 1; }
+            else if (bestc == cl) ++nbest;
+        }
+    }
+    if (nact == 0) return -1;
+    if (nact == 1) return only;
+    if (best >= 0 && nbest == 1) return best;
+    int r = replay_choice(c, col, k);
+    return r < 0 ? -2 : r;
+}
+
+// The reference's sequential sweep (SIG:1948-1991) over one row whose sorted point table is in shared
+// memory; run by ONE thread.  act: scratch for the active list (capacity act_cap).
+__device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* img, uint32_t* out,
+                                            unsigned short* act, int act_cap) {
+    const int w = c.row.w, nsg = c.row.nsg;
+    int nact = 0, sgp = 0, pi = 0;
+    bool overflow = false;
+    for (int col = 0; col < w; ++col) {
+        float color[3] = {0.5f, 0.5f, 0.5f};
+        while (c.sxd[pi] < (double)col) ++pi;
+        --pi;
+        while (c.sxd[pi] < (double)(col + 1)) {
+            double sig;
+            double ctr = visit_ctr(c, col, pi, &sig);
+            while (sgp < nsg && c.sxd[sgp] < ctr) {
+                if (nact < act_cap) act[nact++] = (unsigned short)(c.info[sgp] & 0xFFFFu);
+                else overflow = true;
+                ++sgp;
+            }
+            for (int i = 0; i < nact;) {
+                if ((double)c.px[act[i] + 1] < ctr) { act[i] = act[nact - 1]; --nact; }
+                else ++i;
+            }
+            int best = 0;
+            if (nact != 1) {
+                double bestc = -kEps;
+                for (int i = 0; i < nact; ++i) {
+                    int sp = act[i];
+                    float x0 = c.px[sp], x1 = c.px[sp + 1];
+                    float den = x1 - x0;
+                    double ip = (ctr - (double)x0) / (double)den;
+                    double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+                    double cl = t0 + t1;
+                    if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
+                }
+            }
+            if (nact > 0) {
+                int sp = act[best];
+                int cl = pt_col(sp, c.row), cr = pt_col(sp + 1, c.row);
+                double ip = 0.0;
+                if (cl != cr) {
+                    float den = c.px[sp + 1] - c.px[sp];
+                    ip = (ctr - (double)c.px[sp]) / (double)den;
+                }
+                accumulate(color, img[cl], img[cr], cl == cr, ip, sig);
+            }
+            ++pi;
+        }
+        out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
+    }
+    return overflow;
+}
+
+// One CTA per (row, frame, eye), 512 threads, PER points per thread (512 * PER >= points of the row).
+template <int PER>
+__global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a, int sharp, int* __restrict__ row_flags,
+                                                               int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NP = kPolyThreads * PER;
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
     if (a.eye[eye].passthrough) return;
     RowCtx c;
     c.w = w; c.sharp = sharp != 0; c.npts = (sharp ? 2 * w : w) + 2; c.nsg = c.npts - 1;
     const int npts = c.npts, nsg = c.nsg;
-    float* px = reinterpret_cast<float*>(smem_raw);
-    float* clo = px + npts;
-    float* sx = clo + w;            // [npts] sorted x
-    float* reach = sx + npts;       // [npts] prefix max (sorted order) of segment end x1
-    int* start = reinterpret_cast<int*>(reach + npts);
-    uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));   // [w] RGBX8 row
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(simg + w);
-    unsigned short* tmp = sidx + (npts + (npts & 1));
-    unsigned short* rnk = tmp + (npts + (npts & 1));
-    __shared__ int s_warp[32];
-    __shared__ float s_wmax[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float* px = reinterpret_cast<float*>(smem_raw);                 // [NP]
+    double* sxd = reinterpret_cast<double*>(px + NP);               // [NP]   (aliases pm / sm during the sort)
+    float* pm = reinterpret_cast<float*>(sxd);                      // [NP] inclusive prefix max of px
+    float* sm = pm + NP;                                            // [NP] inclusive suffix min of px
+    uint32_t* info = reinterpret_cast<uint32_t*>(sxd + NP);         // [NP]
+    float* reach = reinterpret_cast<float*>(info + NP);             // [NP]
+    float* clo = reach + NP;                                        // [w]
+    int* start = reinterpret_cast<int*>(clo + w);                   // [w + 4]
+    uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));  // [w]
+    __shared__ float s_wa[16], s_wb[16];
     __shared__ int s_flag;
-    if (threadIdx.x == 0) s_flag = 0;
+    if (tid == 0) s_flag = 0;
+
+    // ---- A: image row, points
     const int64_t row_off = (int64_t)frame * a.h * w + (int64_t)y * w;
-    const uint32_t* img = a.image_u8 + row_off;
-    for (int x = threadIdx.x; x < w; x += blockDim.x) simg[x] = img[x];
-    build_sorted_points(a, eye, frame, y, c, px, clo, sidx, tmp, rnk, start, s_warp);
-
-    // sorted x and the running maximum of segment ends (segment k = sorted point k -> its source successor)
     {
-        const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-        const int per = (npts + kPolyThreads - 1) / kPolyThreads;
-        const int b0 = tid * per, b1 = min(b0 + per, npts);
-        float m = -INFINITY;
-        for (int k = b0; k < b1; ++k) {
-            int sp = sidx[k];
-            sx[k] = px[sp];
-            float x1 = (k < nsg) ? px[sp + 1] : -INFINITY;   // the last sorted point (sentinel 2W) starts no segment
-            m = fmaxf(m, x1);
-            reach[k] = m;
-        }
-        float inc = m;
-        for (int o = 1; o < 32; o <<= 1) {
-            float t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc = fmaxf(inc, t);
-        }
-        if (lane == 31) s_wmax[wid] = inc;
-        __syncthreads();
-        float before = -INFINITY;   // max over all earlier threads
-        for (int q = 0; q < wid; ++q) before = fmaxf(before, s_wmax[q]);
-        float prev = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane > 0) before = fmaxf(before, prev);
-        for (int k = b0; k < b1; ++k) reach[k] = fmaxf(reach[k], before);
-        __syncthreads();
-    }
-
-    uint32_t* out = a.out[eye] + row_off;
-    bool need_exact = false;
-    for (int col = threadIdx.x; col < w; col += blockDim.x) {
-        float color[3] = {0.5f, 0.5f, 0.5f};
-        const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;   // intervals k0..k1 (left point rank)
-        for (int k = k0; k <= k1; ++k) {
-            double pa = (double)sx[k], pb = (double)sx[k + 1];
-            double from = fmax((double)col, pa) + kEps;
-            double to = fmin((double)(col + 1), pb) - kEps;
-            double sig = to - from;
-            double ctr = from + 0.5 * sig;
-            // active set: segments j <= k with x0 < ctr and not x1 < ctr
-            int nact = 0, best = -1, only = -1, nbest = 0;
-            double bestc = -kEps, best_ip = 0.0;
-            for (int j = k; j >= 0 && !((double)reach[j] < ctr); --j) {
-                int sp = sidx[j];
-                float x0 = sx[j], x1 = px[sp + 1];
-                if (!((double)x0 < ctr) || ((double)x1 < ctr)) continue;
-                ++nact;
-                only = sp;
-                float den = x1 - x0;
-                double ip = (ctr - (double)x0) / (double)den;
-                double t0 = (1.0 - ip) * (double)pt_clo(sp, c, clo), t1 = ip * (double)pt_clo(sp + 1, c, clo);
-                double cl = t0 + t1;
-                if (0.0 < ip && ip < 1.0) {
-                    if (bestc < cl) { bestc = cl; best = sp; best_ip = ip; nbest = 1; }
-                    else if (bestc == cl) ++nbest;
-                }
-            }
-            int sp;
-            double ip;
-            if (nact == 1) {
-                sp = only;
-                float den = px[sp + 1] - px[sp];
-                ip = (ctr - (double)px[sp]) / (double)den;
-            } else if (nact == 0) {
-                continue;  // cannot happen inside the sentinels; the reference would read a stale slot
+        const uint32_t* img = a.image_u8 + row_off;
+        const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
+        float scale;
+        const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
+        const float* dep = a.depth[eye] + row_off;
+        for (int col = tid; col < w; col += kPolyThreads) {
+            simg[col] = img[col];
+            float d = dep[col];
+            if (scale != 1.0f) d = d * scale;
+            float nd = norm(d);
+            double an = widen(fabsf(nd));
+            double p;
+            if (a.expo == 2.0) p = an * an;
+            else if (a.expo == 1.0) p = an;
+            else p = pow(an, a.expo);
+            double sp = (nd >= 0.0f) ? p : -p;
+            double cd = sp * div_px;
+            double cx = ((double)col + 0.5) + cd;
+            cx = cx + sep_px;
+            clo[col] = narrow(fabs(cd));
+            if (c.sharp) {
+                px[1 + 2 * col] = narrow(cx - 0.45);
+                px[2 + 2 * col] = narrow(cx + 0.45);
             } else {
-                if (best < 0 || nbest > 1) { need_exact = true; best = (best < 0) ? only : best; }
-                sp = best;
-                ip = best_ip;
-                if (best_ip == 0.0) {
+                px[1 + col] = narrow(cx);
+            }
+        }
+        if (tid == 0) px[0] = (float)(-1.0 * w);
+        for (int i = npts - 1 + tid; i < NP; i += kPolyThreads) px[i] = (i == npts - 1) ? (float)(2.0 * w) : INFINITY;
+        for (int b = tid; b < w + 4; b += kPolyThreads) start[b] = 0;
+    }
+    __syncthreads();
+
+    // ---- B: inclusive prefix max / suffix min of px in source order (thread t owns points t*PER .. t*PER+PER-1)
+    float v[PER], lmax[PER], lmin[PER];
+    const int i0 = tid * PER;
+    {
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q) {
+            float4 t = reinterpret_cast<const float4*>(px + i0)[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) { m = fmaxf(m, v[e]); lmax[e] = m; }
+        float n = INFINITY;
+#pragma unroll
+        for (int e = PER - 1; e >= 0; --e) { n = fminf(n, v[e]); lmin[e] = n; }
+        // warp-level exclusive scans of the per-thread totals
+        float im = m, in_ = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float t = __shfl_up_sync(0xffffffffu, im, o);
+            if (lane >= o) im = fmaxf(im, t);
+            float u = __shfl_down_sync(0xffffffffu, in_, o);
+            if (lane + o < 32) in_ = fminf(in_, u);
+        }
+        if (lane == 31) s_wa[wid] = im;
+        if (lane == 0) s_wb[wid] = in_;
+        float em = __shfl_up_sync(0xffffffffu, im, 1);    // max over earlier lanes of the warp
+        float en = __shfl_down_sync(0xffffffffu, in_, 1); // min over later lanes
+        if (lane == 0) em = -INFINITY;
+        if (lane == 31) en = INFINITY;
+        __syncthreads();
+        for (int q = 0; q < wid; ++q) em = fmaxf(em, s_wa[q]);
+        for (int q = wid + 1; q < kPolyThreads / 32; ++q) en = fminf(en, s_wb[q]);
+#pragma unroll
+        for (int e = 0; e < PER; ++e) { lmax[e] = fmaxf(lmax[e], em); lmin[e] = fminf(lmin[e], en); }
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q) {
+            reinterpret_cast<float4*>(pm + i0)[q] = make_float4(lmax[4 * q], lmax[4 * q + 1], lmax[4 * q + 2], lmax[4 * q + 3]);
+            reinterpret_cast<float4*>(sm + i0)[q] = make_float4(lmin[4 * q], lmin[4 * q + 1], lmin[4 * q + 2], lmin[4 * q + 3]);
+        }
+        // lmax[e] / lmin[e] now hold the INCLUSIVE scans; em / en the exclusive values of the thread's first / last point
+        __syncthreads();
+        // ---- C: stable rank of every point = i - #(earlier, larger) + #(later, smaller)
+        int rk[PER];
+        uint32_t fl[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = i0 + e;
+            const float x = v[e];
+            const float pe = (e == 0) ? em : lmax[e - 1];          // max of all earlier points
+            const float se = (e == PER - 1) ? en : lmin[e + 1];    // min of all later points
+            int r = i;
+            const bool clean = (pe <= x) && (se >= x);
+            if (!clean) {
+                for (int j = i - 1; j >= 0 && pm[j] > x; --j) r -= (px[j] > x) ? 1 : 0;
+                for (int j = i + 1; j < npts && sm[j] < x; ++j) r += (px[j] < x) ? 1 : 0;
+            }
+            rk[e] = r;
+            // "simple": at any centre inside (this point, its sorted successor) exactly one segment is active, the
+            // one that starts here, and it ends at the sorted successor.  True when this point is clean (everything
+            // sorted before it is everything before it in source order) and its source successor is a suffix minimum.
+            uint32_t f = 0;
+            if (clean && i < nsg) {
+                float xn, sn;
+                if (e < PER - 1) { xn = v[e + 1]; sn = lmin[e + 1]; } else { xn = px[i + 1]; sn = sm[i + 1]; }
+                if (xn == sn && xn > x) f = kSimple;
+            }
+            fl[e] = f;
+        }
+        __syncthreads();   // pm / sm are dead from here on: sxd overwrites them
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = i0 + e;
+            if (i < npts) { sxd[rk[e]] = widen(v[e]); info[rk[e]] = (uint32_t)i | fl[e]; }
+        }
+    }
+    __syncthreads();
+
+    // ---- D: reach = prefix max over sorted segments of their end x1; bucket starts
+    {
+        float m = -INFINITY;
+        float loc[PER];
+        int bprev;
+        {
+            int kp = i0 - 1;
+            if (kp < 0) bprev = -1;
+            else if (kp >= npts) bprev = w + 1;
+            else { float fx = floorf(px[info[kp] & 0xFFFFu]); bprev = (fx < 0.0f) ? 0 : ((fx >= (float)w) ? w + 1 : (int)fx + 1); }
+        }
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int k = i0 + e;
+            float x1 = -INFINITY;
+            if (k < npts) {
+                const int sp = (int)(info[k] & 0xFFFFu);
+                if (k < nsg) x1 = px[sp + 1];
+                float fx = floorf(px[sp]);
+                int b = (fx < 0.0f) ? 0 : ((fx >= (float)w) ? w + 1 : (int)fx + 1);
+                for (int q = bprev + 1; q <= b; ++q) start[q] = k;
+                bprev = b;
+                if (k == npts - 1) start[w + 2] = npts;
+            }
+            m = fmaxf(m, x1);
+            loc[e] = m;
+        }
+        float im = m;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float t = __shfl_up_sync(0xffffffffu, im, o);
+            if (lane >= o) im = fmaxf(im, t);
+        }
+        if (lane == 31) s_wa[wid] = im;
+        float em = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane == 0) em = -INFINITY;
+        __syncthreads();
+        for (int q = 0; q < wid; ++q) em = fmaxf(em, s_wa[q]);
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q)
+            reinterpret_cast<float4*>(reach + i0)[q] = make_float4(fmaxf(loc[4 * q], em), fmaxf(loc[4 * q + 1], em),
+                                                                   fmaxf(loc[4 * q + 2], em), fmaxf(loc[4 * q + 3], em));
+    }
+    __syncthreads();
+
+    // ---- E: sweep, one thread per output column
+    PolyCtx ctx;
+    ctx.px = px; ctx.sxd = sxd; ctx.info = info; ctx.reach = reach; ctx.clo = clo; ctx.start = start; ctx.row = c;
+    uint32_t* out = a.out[eye] + row_off;
+    bool give_up = false;
+    for (int col = tid; col < w; col += kPolyThreads) {
+        double c0 = 0.5, c1 = 0.5, c2 = 0.5;   // float32-valued accumulators kept in float64 registers
+        const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;
+        const double cold = (double)col, col1d = (double)(col + 1);
+        double pa = sxd[k0];
+        for (int k = k0; k <= k1; ++k) {
+            const double pb = sxd[k + 1];
+            const double from = fmax(cold, pa) + kEps;
+            const double to = fmin(col1d, pb) - kEps;
+            const double sig = to - from;
+            const uint32_t inf = info[k];
+            int sp = (int)(inf & 0xFFFFu);
+            double ip = 0.0;
+            bool have_ip = false;
+            if (!((inf & kSimple) && sig > 0.0)) {
+                const double ctr = from + 0.5 * sig;
+                sp = general_visit(ctx, col, k, ctr);
+                if (sp == -2) { give_up = true; sp = -1; }
+                if (sp < 0) { pa = pb; continue; }
+                if (pt_col(sp, c) != pt_col(sp + 1, c)) {
                     float den = px[sp + 1] - px[sp];
                     ip = (ctr - (double)px[sp]) / (double)den;
+                    have_ip = true;
                 }
             }
-            int cl = pt_col(sp, c), cr = pt_col(sp + 1, c);
-            accumulate(color, simg[cl], simg[cr], cl == cr, ip, sig);
+            const int cl = pt_col(sp, c), cr = pt_col(sp + 1, c);
+            const uint32_t pl = simg[cl];
+            if (cl == cr) {
+                c0 = round24(c0 + u8_to_f64(pl & 255u) * sig);
+                c1 = round24(c1 + u8_to_f64((pl >> 8) & 255u) * sig);
+                c2 = round24(c2 + u8_to_f64((pl >> 16) & 255u) * sig);
+            } else {
+                if (!have_ip) {   // simple: the segment is (pa, pb)
+                    const double ctr = from + 0.5 * sig;
+                    const double den = round24(pb - pa);   // the reference's float32 subtraction x1 - x0
+                    ip = (ctr - pa) / den;
+                }
+                const uint32_t pr = simg[cr];
+                const double om = 1.0 - ip;
+                {
+                    double t0 = u8_to_f64(pl & 255u) * om, t1 = u8_to_f64(pr & 255u) * ip;
+                    double mix = t0 + t1;
+                    c0 = round24(c0 + mix * sig);
+                }
+                {
+                    double t0 = u8_to_f64((pl >> 8) & 255u) * om, t1 = u8_to_f64((pr >> 8) & 255u) * ip;
+                    double mix = t0 + t1;
+                    c1 = round24(c1 + mix * sig);
+                }
+                {
+                    double t0 = u8_to_f64((pl >> 16) & 255u) * om, t1 = u8_to_f64((pr >> 16) & 255u) * ip;
+                    double mix = t0 + t1;
+                    c2 = round24(c2 + mix * sig);
+                }
+            }
+            pa = pb;
         }
-        out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
+        out[col] = pack_rgbx(__double2int_rz(c0), __double2int_rz(c1), __double2int_rz(c2));
     }
-    if (need_exact) s_flag = 1;
+    if (give_up) s_flag = 1;
     __syncthreads();
-    if (threadIdx.x == 0) row_flags[((int64_t)frame * 2 + eye) * a.h + y] = s_flag;
+    const int flagged = s_flag;
+    if (tid == 0) {
+        if (row_flags) row_flags[((int64_t)frame * 2 + eye) * a.h + y] = flagged;
+        if (flagged) {
+            // the list replay did not fit its budget somewhere in this row: redo the row sequentially
+            // (reach[] is dead now and serves as the active list)
+            bool ovf = sequential_row(ctx, simg, out, reinterpret_cast<unsigned short*>(reach), 2 * NP);
+            if (ovf) atomicOr(status, 1);
+        }
+    }
+}
+
+template <int PER>
+static size_t fast_smem_per(int w) {
+    return (size_t)kPolyThreads * PER * (4 + 8 + 4 + 4) + (size_t)w * 4 + (size_t)(w + 4) * 4 + (size_t)w * 4;
 }
 
 static size_t exact_smem(int w, int sharp, int act_cap) {
@@ -377,46 +743,47 @@ static size_t exact_smem(int w, int sharp, int act_cap) {
     size_t np2 = npts + (npts & 1);
     return npts * 4 + (size_t)w * 4 + (size_t)(w + 4) * 4 + np2 * 2 * 3 + (size_t)act_cap * 2;
 }
-static size_t fast_smem(int w, int sharp) {
-    size_t npts = (size_t)(sharp ? 2 * w : w) + 2;
-    size_t np2 = npts + (npts & 1);
-    return npts * 4 * 3 + (size_t)w * 4 + (size_t)(w + 4) * 4 + (size_t)w * 4 + np2 * 2 * 3;
-}
-
 size_t polylines_scratch_bytes(int n, int h) { return ((size_t)n * 2 * h + 16) * sizeof(int); }
 
-// scratch: [n*2*h] row flags + [1] status word.  force_exact = 1 skips the fast sweep (tests).
+template <int PER>
+static cudaError_t launch_fast(const WarpArgs& a, int sharp, int* flags, int* status, cudaStream_t s) {
+    const size_t fs = fast_smem_per<PER>(a.w);
+    cudaError_t e = cudaFuncSetAttribute(k_polylines<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
+    if (e != cudaSuccess) return e;
+    prof_begin(K_POLY_FAST, s);
+    k_polylines<PER><<<dim3(a.h, a.n, 2), kPolyThreads, fs, s>>>(a, sharp, flags, status);
+    prof_end(K_POLY_FAST, s);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// scratch: [n*2*h] row flags + [1] status word.  flags bit 0 = replay every row with the sequential kernel (tests).
 cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s) {
     const int sharp = a.fill == CS_FILL_POLYLINES_SHARP;
     const int w = a.w;
     if (a.scratch_bytes < polylines_scratch_bytes(a.n, a.h)) return cudaErrorInvalidValue;
-    if ((sharp ? 2 * w : w) + 2 > 65535) return cudaErrorInvalidValue;
+    const int npts = (sharp ? 2 * w : w) + 2;
+    if (npts > 65535) return cudaErrorInvalidValue;
     int* flags = reinterpret_cast<int*>(a.scratch);
     int* status = flags + (size_t)a.n * 2 * a.h;
+    const size_t kMaxSmem = 227 * 1024;
+    const bool force_exact = (a.flags & 1) != 0;
+    if (!force_exact) {
+        if (npts <= kPolyThreads * 4 && fast_smem_per<4>(w) <= kMaxSmem) return launch_fast<4>(a, sharp, flags, status, s);
+        if (npts <= kPolyThreads * 8 && fast_smem_per<8>(w) <= kMaxSmem) return launch_fast<8>(a, sharp, flags, status, s);
+        if (npts <= kPolyThreads * 16 && fast_smem_per<16>(w) <= kMaxSmem) return launch_fast<16>(a, sharp, flags, status, s);
+    }
+    // rows too wide for the fast kernel's shared-memory tables (or the test hook): sequential kernel
     double dmax = fmax(fabs(a.eye[0].div_px), fabs(a.eye[1].div_px));
     long long cap_ref = 5ll * (long long)dmax + 25;    // the reference's own list capacity, SIG:1947
-    const size_t kMaxSmem = 227 * 1024;
     size_t base = exact_smem(w, sharp, 0);
     if (base + 64 > kMaxSmem) return cudaErrorInvalidValue;
     long long cap_fit = (long long)((kMaxSmem - base) / 2);
     int act_cap = (int)(cap_ref < cap_fit ? cap_ref : cap_fit);
-    dim3 grid(a.h, a.n, 2);
-    const bool force_exact = (a.flags & 1) != 0;
-    const size_t fs = fast_smem(w, sharp);
-    const bool use_fast = !force_exact && fs <= kMaxSmem;
-    cudaError_t e;
-    if (use_fast) {
-        if (fs > 48 * 1024) cudaFuncSetAttribute(k_polylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
-        prof_begin(K_POLY_FAST, s);
-        k_polylines<<<grid, kPolyThreads, fs, s>>>(a, sharp, flags);
-        prof_end(K_POLY_FAST, s);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
     size_t es = exact_smem(w, sharp, act_cap);
     if (es > 48 * 1024) cudaFuncSetAttribute(k_polylines_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
     prof_begin(K_POLY_EXACT, s);
-    k_polylines_exact<<<grid, kPolyThreads, es, s>>>(a, sharp, act_cap, use_fast ? flags : nullptr, status);
+    k_polylines_exact<<<dim3(a.h, a.n, 2), kPolyThreads, es, s>>>(a, sharp, act_cap, nullptr, status);
     prof_end(K_POLY_EXACT, s);
     count_launch();
     return cudaGetLastError();
