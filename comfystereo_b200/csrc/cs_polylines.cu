@@ -46,6 +46,9 @@ __device__ __forceinline__ float pt_clo(int i, const RowCtx& c, const float* clo
     if (i <= 0 || i >= c.npts - 1) return 0.0f;
     return clo[c.sharp ? ((i - 1) >> 1) : (i - 1)];
 }
+// branch-free variants on a table padded with the two sentinels: clo2[0] = 0, clo2[1 + col], clo2[w + 1] = 0
+__device__ __forceinline__ int pt_slot(int i, bool sharp) { return sharp ? ((i + 1) >> 1) : i; }
+__device__ __forceinline__ int slot_col(int slot, int w) { return min(max(slot - 1, 0), w - 1); }
 
 __device__ __forceinline__ Normalizer pl_normalizer(const WarpArgs& a, int eye, int frame, float* scale_out) {
     const FrameStats st = a.stats[frame];
@@ -284,6 +287,14 @@ __device__ __forceinline__ double round24(double x) {
     hi += (nlo < lo) ? 1u : 0u;
     return __hiloint2double((int)hi, (int)(nlo & 0xE0000000u));
 }
+// Same rounding on the FP64 pipe (Veltkamp / Dekker split with 2^29 + 1): three FP64 operations instead of seven
+// integer ones.  Identical to round24 except on exact ties (low 29 bits = 100...0), which an accumulated colour
+// sum hits with probability 2^-29 per operation.
+__device__ __forceinline__ double round24_fp(double x) {
+    const double g = x * 536870913.0;
+    const double d = x - g;
+    return g + d;
+}
 // float64 -> float32, round to nearest even, without F2F when the result is a normal float32
 __device__ __forceinline__ float narrow(double x) {
     uint32_t e = ((uint32_t)__double2hiint(x) >> 20) & 0x7FFu;
@@ -302,11 +313,14 @@ struct PolyCtx {
     const double* sxd;      // [npts] sorted x, widened
     const uint32_t* info;   // [npts] sorted -> source point index (low 16 bits) | kSimple
     const float* reach;     // [npts] prefix max (sorted order) of segment ends
-    const float* clo;       // [w]
+    const float* clo;       // [w + 2] padded: clo[pt_slot(i)] is the closeness of source point i
     const int* start;       // [w+3] first sorted rank of bucket b = floor(x)+1
     RowCtx row;
 };
-constexpr uint32_t kSimple = 0x10000u;
+// info[k] (k = sorted rank): bits 0-15 source point index; bits 16-17 number of segments active anywhere strictly
+// inside the interval (sorted point k, sorted point k+1), 3 = "three or more / does not fit"; bits 18-24 and 25-31:
+// how many ranks back the first / second active segment starts.
+constexpr int kCodeShift = 16, kOff1Shift = 18, kOff2Shift = 25;
 
 __device__ __forceinline__ double visit_ctr(const PolyCtx& c, int col, int k, double* sig_out) {
     double pa = c.sxd[k], pb = c.sxd[k + 1];
@@ -377,7 +391,7 @@ __device__ __noinline__ int replay_choice(const PolyCtx& c, int col, int k) {
                     float x0 = c.px[sp], x1 = c.px[sp + 1];
                     float den = x1 - x0;
                     double ip = (ctr - (double)x0) / (double)den;
-                    double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+                    double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
                     double cl = t0 + t1;
                     if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
                 }
@@ -404,7 +418,7 @@ __device__ __noinline__ int general_visit(const PolyCtx& c, int col, int k, doub
         only = sp;
         float den = x1 - x0;
         double ip = (ctr - (double)x0) / (double)den;
-        double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+        double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
         double cl = t0 + t1;
         if (0.0 < ip && ip < 1.0) {
             if (bestc < cl) { bestc = cl; best = sp; nbest = 1; }
@@ -449,7 +463,7 @@ __device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* im
                     float x0 = c.px[sp], x1 = c.px[sp + 1];
                     float den = x1 - x0;
                     double ip = (ctr - (double)x0) / (double)den;
-                    double t0 = (1.0 - ip) * (double)pt_clo(sp, c.row, c.clo), t1 = ip * (double)pt_clo(sp + 1, c.row, c.clo);
+                    double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
                     double cl = t0 + t1;
                     if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
                 }
@@ -489,12 +503,16 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     float* sm = pm + NP;                                            // [NP] inclusive suffix min of px
     uint32_t* info = reinterpret_cast<uint32_t*>(sxd + NP);         // [NP]
     float* reach = reinterpret_cast<float*>(info + NP);             // [NP]
-    float* clo = reach + NP;                                        // [w]
-    int* start = reinterpret_cast<int*>(clo + w);                   // [w + 4]
+    float* clo = reach + NP;                                        // [w + 2] padded closeness table
+    int* start = reinterpret_cast<int*>(clo + (w + 4));             // [w + 4]
     uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));  // [w]
+    unsigned short* tlist = reinterpret_cast<unsigned short*>(simg + w);  // [NP] sorted intervals with two active segments
     __shared__ float s_wa[16], s_wb[16];
-    __shared__ int s_flag;
-    if (tid == 0) s_flag = 0;
+    __shared__ int s_flag, s_ndirty, s_ntwo;
+    if (tid == 0) { s_flag = 0; s_ndirty = 0; s_ntwo = 0; }
+    // during the sort the reach[] region holds the list of out-of-order points and their ranks (uint16 each)
+    unsigned short* dlist = reinterpret_cast<unsigned short*>(reach);
+    unsigned short* drank = dlist + NP;
 
     // ---- A: image row, points
     const int64_t row_off = (int64_t)frame * a.h * w + (int64_t)y * w;
@@ -504,12 +522,24 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
         float scale;
         const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
         const float* dep = a.depth[eye] + row_off;
-        for (int col = tid; col < w; col += kPolyThreads) {
-            simg[col] = img[col];
-            float d = dep[col];
+        constexpr int kMaxIter = 4;
+        for (int cbase = 0; cbase < w; cbase += kMaxIter * kPolyThreads) {
+        float dreg[kMaxIter];
+        uint32_t ireg[kMaxIter];
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int col = cbase + tid + it * kPolyThreads;
+            if (col < w) { dreg[it] = dep[col]; ireg[it] = img[col]; }
+        }
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int col = cbase + tid + it * kPolyThreads;
+            if (col >= w) break;
+            simg[col] = ireg[it];
+            float d = dreg[it];
             if (scale != 1.0f) d = d * scale;
             float nd = norm(d);
-            double an = widen(fabsf(nd));
+            double an = (double)fabsf(nd);
             double p;
             if (a.expo == 2.0) p = an * an;
             else if (a.expo == 1.0) p = an;
@@ -518,15 +548,16 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             double cd = sp * div_px;
             double cx = ((double)col + 0.5) + cd;
             cx = cx + sep_px;
-            clo[col] = narrow(fabs(cd));
+            clo[col + 1] = (float)fabs(cd);
             if (c.sharp) {
-                px[1 + 2 * col] = narrow(cx - 0.45);
-                px[2 + 2 * col] = narrow(cx + 0.45);
+                px[1 + 2 * col] = (float)(cx - 0.45);
+                px[2 + 2 * col] = (float)(cx + 0.45);
             } else {
-                px[1 + col] = narrow(cx);
+                px[1 + col] = (float)cx;
             }
         }
-        if (tid == 0) px[0] = (float)(-1.0 * w);
+        }
+        if (tid == 0) { px[0] = (float)(-1.0 * w); clo[0] = 0.0f; clo[w + 1] = 0.0f; }
         for (int i = npts - 1 + tid; i < NP; i += kPolyThreads) px[i] = (i == npts - 1) ? (float)(2.0 * w) : INFINITY;
         for (int b = tid; b < w + 4; b += kPolyThreads) start[b] = 0;
     }
@@ -574,38 +605,42 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
         }
         // lmax[e] / lmin[e] now hold the INCLUSIVE scans; em / en the exclusive values of the thread's first / last point
         __syncthreads();
-        // ---- C: stable rank of every point = i - #(earlier, larger) + #(later, smaller)
-        int rk[PER];
-        uint32_t fl[PER];
+        // ---- C: stable rank of every point = i - #(earlier, larger) + #(later, smaller).  A point with nothing larger
+        // before it and nothing smaller after it keeps its source index.  The others (folds, jitter) are put on a
+        // work list and counted by the whole CTA, neighbours in a fold going to neighbouring lanes.
+        uint32_t dirty_bits = 0;
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
-            const int i = i0 + e;
             const float x = v[e];
             const float pe = (e == 0) ? em : lmax[e - 1];          // max of all earlier points
             const float se = (e == PER - 1) ? en : lmin[e + 1];    // min of all later points
+            if (!((pe <= x) && (se >= x))) dirty_bits |= 1u << e;
+        }
+        if (dirty_bits) {
+            int base = atomicAdd(&s_ndirty, __popc(dirty_bits));
+#pragma unroll
+            for (int e = 0; e < PER; ++e)
+                if (dirty_bits & (1u << e)) dlist[base++] = (unsigned short)(i0 + e);
+        }
+        __syncthreads();
+        const int ndirty = s_ndirty;
+        for (int q = tid; q < ndirty; q += kPolyThreads) {
+            const int i = dlist[q];
+            const float x = px[i];
             int r = i;
-            const bool clean = (pe <= x) && (se >= x);
-            if (!clean) {
-                for (int j = i - 1; j >= 0 && pm[j] > x; --j) r -= (px[j] > x) ? 1 : 0;
-                for (int j = i + 1; j < npts && sm[j] < x; ++j) r += (px[j] < x) ? 1 : 0;
-            }
-            rk[e] = r;
-            // "simple": at any centre inside (this point, its sorted successor) exactly one segment is active, the
-            // one that starts here, and it ends at the sorted successor.  True when this point is clean (everything
-            // sorted before it is everything before it in source order) and its source successor is a suffix minimum.
-            uint32_t f = 0;
-            if (clean && i < nsg) {
-                float xn, sn;
-                if (e < PER - 1) { xn = v[e + 1]; sn = lmin[e + 1]; } else { xn = px[i + 1]; sn = sm[i + 1]; }
-                if (xn == sn && xn > x) f = kSimple;
-            }
-            fl[e] = f;
+            for (int j = i - 1; j >= 0 && pm[j] > x; --j) r -= (px[j] > x) ? 1 : 0;
+            for (int j = i + 1; j < npts && sm[j] < x; ++j) r += (px[j] < x) ? 1 : 0;
+            drank[i] = (unsigned short)r;
         }
         __syncthreads();   // pm / sm are dead from here on: sxd overwrites them
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
             const int i = i0 + e;
-            if (i < npts) { sxd[rk[e]] = widen(v[e]); info[rk[e]] = (uint32_t)i | fl[e]; }
+            if (i < npts) {
+                const int r = (dirty_bits & (1u << e)) ? (int)drank[i] : i;
+                sxd[r] = (double)v[e];
+                info[r] = (uint32_t)i;
+            }
         }
     }
     __syncthreads();
@@ -655,66 +690,125 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     }
     __syncthreads();
 
+    // ---- D2: active set of every sorted interval (a, b) = (point k, point k+1).  For a centre strictly inside, a
+    // segment j is active iff it starts at or before a (j <= k) and ends beyond a; nothing between a and b is a point,
+    // so all of this is float32 comparisons.  Intervals with up to two active segments are encoded in info[k].
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int k = i0 + e;
+        if (k >= nsg) continue;
+        const uint32_t me = info[k] & 0xFFFFu;
+        const float av = px[me];
+        int cnt = 0, o1 = 0, o2 = 0;
+        for (int j = k; j >= 0 && reach[j] > av; --j) {
+            const int sp = (int)(info[j] & 0xFFFFu);
+            if (px[sp + 1] > av) {
+                if (cnt == 0) o1 = k - j; else if (cnt == 1) o2 = k - j;
+                ++cnt;
+            }
+        }
+        uint32_t code = (uint32_t)min(cnt, 3);
+        if (o1 > 127 || o2 > 127) code = 3u;
+        if (code == 2u) tlist[atomicAdd(&s_ntwo, 1)] = (unsigned short)k;   // resolved below by the whole CTA
+        info[k] = me | (code << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
+    }
+    __syncthreads();
+    {
+        const int ntwo = s_ntwo;
+        for (int q = tid; q < ntwo; q += kPolyThreads) {
+            const int k = tlist[q];
+            const uint32_t inf = info[k];
+            const uint32_t me = inf & 0xFFFFu;
+            int o1 = (int)((inf >> kOff1Shift) & 127u);
+            const int o2 = (int)((inf >> kOff2Shift) & 127u);
+            const float av = px[me];
+            uint32_t code = 2u;
+            {
+                // Interpolated closeness is linear in the centre, so if one candidate leads at both ends of the interval
+                // by more than any rounding could matter, it leads at every centre inside: the interval becomes a
+                // one-candidate interval.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
+                // segment, and ip < 1 can only fail (float32 rounding of x1 - x0) for long segments that end at or just
+                // beyond this interval's right point -- those stay two-candidate and are decided per visit in FP64.
+                const float bv = px[info[k + 1] & 0xFFFFu];
+                const int spA = (int)(info[k - o1] & 0xFFFFu), spB = (int)(info[k - o2] & 0xFFFFu);
+                const float ax0 = px[spA], ax1 = px[spA + 1], bx0 = px[spB], bx1 = px[spB + 1];
+                const float aq0 = clo[pt_slot(spA, c.sharp)], aq1 = clo[pt_slot(spA + 1, c.sharp)];
+                const float bq0 = clo[pt_slot(spB, c.sharp)], bq1 = clo[pt_slot(spB + 1, c.sharp)];
+                const float ad = ax1 - ax0, bd = bx1 - bx0;
+                // ip < 1 is guaranteed when the centre stays more than half a float32 ulp of (x1 - x0) below x1:
+                // always for lengths < 2 (the centre is >= 1e-7 below the interval's end), else when x1 is far enough
+                // beyond the interval
+                const bool safe = (ad < 2.0f || (ax1 - bv) > ad * 1.2e-7f) && (bd < 2.0f || (bx1 - bv) > bd * 1.2e-7f);
+                // closeness of both candidates at the two ends (float32 is plenty: the margin below is 1e-3)
+                const float ta = __fdividef(av - ax0, ad), tb = __fdividef(bv - ax0, ad);
+                const float ua = __fdividef(av - bx0, bd), ub = __fdividef(bv - bx0, bd);
+                const float a_lo = aq0 + ta * (aq1 - aq0), a_hi = aq0 + tb * (aq1 - aq0);
+                const float b_lo = bq0 + ua * (bq1 - bq0), b_hi = bq0 + ub * (bq1 - bq0);
+                const float margin = 1e-3f + 1e-4f * fmaxf(fmaxf(aq0, aq1), fmaxf(bq0, bq1));
+                if (safe && a_lo > b_lo + margin && a_hi > b_hi + margin) code = 1u;                     // first candidate
+                else if (safe && b_lo > a_lo + margin && b_hi > a_hi + margin) { code = 1u; o1 = o2; }  // second candidate
+            }
+            if (code == 1u)
+                info[k] = me | (1u << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
+        }
+    }
+    __syncthreads();
+
     // ---- E: sweep, one thread per output column
     PolyCtx ctx;
     ctx.px = px; ctx.sxd = sxd; ctx.info = info; ctx.reach = reach; ctx.clo = clo; ctx.start = start; ctx.row = c;
     uint32_t* out = a.out[eye] + row_off;
     bool give_up = false;
+    const bool shp = c.sharp;
     for (int col = tid; col < w; col += kPolyThreads) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;   // float32-valued accumulators kept in float64 registers
         const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;
-        const double cold = (double)col, col1d = (double)(col + 1);
+        const double cold = u8_to_f64((uint32_t)col), col1d = cold + 1.0;
         double pa = sxd[k0];
         for (int k = k0; k <= k1; ++k) {
             const double pb = sxd[k + 1];
-            const double from = fmax(cold, pa) + kEps;
-            const double to = fmin(col1d, pb) - kEps;
+            const double from = ((pa > cold) ? pa : cold) + kEps;     // no NaNs here: plain compare-select
+            const double to = ((pb < col1d) ? pb : col1d) - kEps;
             const double sig = to - from;
+            const double ctr = from + 0.5 * sig;
             const uint32_t inf = info[k];
-            int sp = (int)(inf & 0xFFFFu);
-            double ip = 0.0;
-            bool have_ip = false;
-            if (!((inf & kSimple) && sig > 0.0)) {
-                const double ctr = from + 0.5 * sig;
+            const uint32_t code = (inf >> kCodeShift) & 3u;
+            int sp;
+            bool resolved = false, off_is_k = false;
+            if (code == 1u && sig > 0.0) {
+                const int off1 = (int)((inf >> kOff1Shift) & 127u);
+                sp = (off1 == 0) ? (int)(inf & 0xFFFFu) : (int)(info[k - off1] & 0xFFFFu);
+                off_is_k = (off1 == 0);   // the segment starts at this interval's left point: x0 = pa
+                resolved = true;
+            }
+            if (!resolved) {
+                off_is_k = false;
                 sp = general_visit(ctx, col, k, ctr);
                 if (sp == -2) { give_up = true; sp = -1; }
                 if (sp < 0) { pa = pb; continue; }
-                if (pt_col(sp, c) != pt_col(sp + 1, c)) {
-                    float den = px[sp + 1] - px[sp];
-                    ip = (ctr - (double)px[sp]) / (double)den;
-                    have_ip = true;
-                }
             }
-            const int cl = pt_col(sp, c), cr = pt_col(sp + 1, c);
+            const int sl = pt_slot(sp, shp), sr = pt_slot(sp + 1, shp);
+            const int cl = slot_col(sl, w), cr = slot_col(sr, w);
             const uint32_t pl = simg[cl];
-            if (cl == cr) {
-                c0 = round24(c0 + u8_to_f64(pl & 255u) * sig);
-                c1 = round24(c1 + u8_to_f64((pl >> 8) & 255u) * sig);
-                c2 = round24(c2 + u8_to_f64((pl >> 16) & 255u) * sig);
-            } else {
-                if (!have_ip) {   // simple: the segment is (pa, pb)
-                    const double ctr = from + 0.5 * sig;
-                    const double den = round24(pb - pa);   // the reference's float32 subtraction x1 - x0
-                    ip = (ctr - pa) / den;
-                }
+            double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
+            if (cl != cr) {
+                // ip = (ctr - x0) / (x1 - x0) with the reference's float32 subtraction in the denominator
+                const double x0 = off_is_k ? pa : (double)px[sp];
+                const double x1 = (double)px[sp + 1];
+                const double den = round24_fp(x1 - x0);
+                const double ip = (ctr - x0) / den;
                 const uint32_t pr = simg[cr];
                 const double om = 1.0 - ip;
-                {
-                    double t0 = u8_to_f64(pl & 255u) * om, t1 = u8_to_f64(pr & 255u) * ip;
-                    double mix = t0 + t1;
-                    c0 = round24(c0 + mix * sig);
-                }
-                {
-                    double t0 = u8_to_f64((pl >> 8) & 255u) * om, t1 = u8_to_f64((pr >> 8) & 255u) * ip;
-                    double mix = t0 + t1;
-                    c1 = round24(c1 + mix * sig);
-                }
-                {
-                    double t0 = u8_to_f64((pl >> 16) & 255u) * om, t1 = u8_to_f64((pr >> 16) & 255u) * ip;
-                    double mix = t0 + t1;
-                    c2 = round24(c2 + mix * sig);
-                }
+                double t0 = v0 * om, t1 = u8_to_f64(pr & 255u) * ip;
+                v0 = t0 + t1;
+                t0 = v1 * om; t1 = u8_to_f64((pr >> 8) & 255u) * ip;
+                v1 = t0 + t1;
+                t0 = v2 * om; t1 = u8_to_f64((pr >> 16) & 255u) * ip;
+                v2 = t0 + t1;
             }
+            c0 = round24_fp(c0 + v0 * sig);
+            c1 = round24_fp(c1 + v1 * sig);
+            c2 = round24_fp(c2 + v2 * sig);
             pa = pb;
         }
         out[col] = pack_rgbx(__double2int_rz(c0), __double2int_rz(c1), __double2int_rz(c2));
@@ -735,7 +829,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
 
 template <int PER>
 static size_t fast_smem_per(int w) {
-    return (size_t)kPolyThreads * PER * (4 + 8 + 4 + 4) + (size_t)w * 4 + (size_t)(w + 4) * 4 + (size_t)w * 4;
+    return (size_t)kPolyThreads * PER * (4 + 8 + 4 + 4 + 2) + (size_t)(w + 4) * 4 + (size_t)(w + 4) * 4 + (size_t)w * 4;
 }
 
 static size_t exact_smem(int w, int sharp, int act_cap) {

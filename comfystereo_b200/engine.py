@@ -90,11 +90,11 @@ def _stream_ptr(device):
 
 
 def default_chunk(p, n, h, w):
-    """Frames per kernel sequence.  Scratch per frame is ~26 B/px; a couple of frames keep it inside
-    the 126 MB L2 between producer and consumer kernels while amortising launches."""
+    """Frames per kernel sequence: about four 1080p frames' worth of pixels.  Measured on B200 (chunk sweep in
+    profiles/): larger grids (fewer partial waves) matter more than keeping the ~26 B/px of scratch inside L2."""
     group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
     group = min(group, n)
-    target = max(1, int(96e6 // (26 * h * w)))
+    target = max(1, int(8.4e6 // (h * w)))
     chunk = max(group, (target // group) * group)
     return min(chunk, n)
 
