@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
     float* s_vl = s_row + kSeg + bs;
     float* s_vr = s_vl + kSeg;
     __shared__ float s_red[4][kSeg / 32];
+    // the weight LUT is indexed by a per-lane distance: from the kernel-parameter (constant) bank that serialises
+    // one replay per distinct index, from shared memory it is a plain gather
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = lut.w[threadIdx.x];
+    __syncthreads();
     const int frame = blockIdx.y;
     const float scale = frame_scale(st, frame, scale_mode, group, n);
     const float wv = 1.0f / (float)(2 * v + 1);
@@ -162,12 +167,12 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
                 wl = 0.0f; wr = 0.0f;
                 const int y0 = max(y - v, 0), y1 = min(y + v, h - 1);
                 for (int yy = y0; yy <= y1; ++yy) {
-                    wl = fmaf(lut.w[dl[(int64_t)yy * w + x]], wv, wl);
-                    wr = fmaf(lut.w[dr[(int64_t)yy * w + x]], wv, wr);
+                    wl = fmaf(s_lut[dl[(int64_t)yy * w + x]], wv, wl);
+                    wr = fmaf(s_lut[dr[(int64_t)yy * w + x]], wv, wr);
                 }
             } else {
-                wl = lut.w[dl[(int64_t)y * w + x]];
-                wr = lut.w[dr[(int64_t)y * w + x]];
+                wl = s_lut[dl[(int64_t)y * w + x]];
+                wr = s_lut[dr[(int64_t)y * w + x]];
             }
             float b = 0.0f;
             for (int k = 0; k < bs; ++k) b = fmaf(s_row[threadIdx.x + k], wb, b);
