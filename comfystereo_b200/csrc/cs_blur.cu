@@ -121,99 +121,148 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
 }
 
 // ------------------------------------------------------------------------------------ blend
-constexpr int kSeg = 256;  // pixels per work item = threads per CTA
+constexpr int kSeg = 256;  // pixels per row segment = threads per CTA
+constexpr int kTileY = 8;  // rows per work item
 
+// Work item = kTileY rows x kSeg columns.  The LUT weights of the kTileY + 2v rows the vertical box touches and
+// the kTileY depth row segments (with the horizontal box's halo) are staged in shared memory once, so every tap
+// of both boxes is one LDS + one FFMA.  Rows outside the image hold weight 0: fmaf(0, wv, acc) == acc, which is
+// the reference's zero padding.  Tap order (ascending, fmaf) is the oracle's.
 __global__ void __launch_bounds__(kSeg) k_blur_blend(
     const float* __restrict__ gray, FrameStats* __restrict__ st, int scale_mode, int group, int n,
     int h, int w, int bs, int radius, int v, const __grid_constant__ BlurLut lut,
     const uint8_t* __restrict__ dist_l, const uint8_t* __restrict__ dist_r, float* __restrict__ blur_l,
     float* __restrict__ blur_r, float* __restrict__ out_l, float* __restrict__ out_r, int items_per_frame,
     int segs_per_row) {
-    extern __shared__ float s_row[];  // [kSeg + bs] depth row segment with halo, then 2*kSeg output staging
-    float* s_vl = s_row + kSeg + bs;
-    float* s_vr = s_vl + kSeg;
+    extern __shared__ float s_dyn[];
+    const int wrows = kTileY + 2 * v;
+    float* s_wl = s_dyn;                         // [wrows][kSeg]
+    float* s_wr = s_wl + wrows * kSeg;           // [wrows][kSeg]
+    float* s_row = s_wr + wrows * kSeg;          // [kTileY][kSeg + bs]
+    float* s_vl = s_wl;                          // output staging reuses the weight tiles: [kTileY][kSeg] x 2
+    float* s_vr = s_wl + kTileY * kSeg;
     __shared__ float s_red[4][kSeg / 32];
-    // the weight LUT is indexed by a per-lane distance: from the kernel-parameter (constant) bank that serialises
-    // one replay per distinct index, from shared memory it is a plain gather
     __shared__ float s_lut[256];
-    s_lut[threadIdx.x] = lut.w[threadIdx.x];
-    __syncthreads();
+    const int tid = threadIdx.x;
+    s_lut[tid] = lut.w[tid];
     const int frame = blockIdx.y;
     const float scale = frame_scale(st, frame, scale_mode, group, n);
     const float wv = 1.0f / (float)(2 * v + 1);
     const float wb = 1.0f / (float)bs;
     const int lo = bs / 2;
+    const int rw = kSeg + bs;
     const uint64_t pol = policy_evict_first();
     const float* base = gray + (int64_t)frame * h * w;
     const uint8_t* dl = dist_l + (int64_t)frame * h * w;
     const uint8_t* dr = dist_r + (int64_t)frame * h * w;
+    float* bl = blur_l + (int64_t)frame * h * w;
+    float* br = blur_r + (int64_t)frame * h * w;
     const bool vec_out = out_l && (w % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0);
+    __syncthreads();
 
     float mnl = INFINITY, mxl = -INFINITY, mnr = INFINITY, mxr = -INFINITY;
     for (int item = blockIdx.x; item < items_per_frame; item += gridDim.x) {
-        const int y = item / segs_per_row, x0 = (item - y * segs_per_row) * kSeg;
-        const float* row = base + (int64_t)y * w;
-        // stage depth[x0 - lo .. x0 + kSeg + bs - lo) (zeros outside the row)
-        for (int i = threadIdx.x; i < kSeg + bs; i += kSeg) {
-            int xx = x0 - lo + i;
-            s_row[i] = (xx >= 0 && xx < w) ? scaled(row[xx], scale) : 0.0f;
+        const int ty = item / segs_per_row, x0 = (item - ty * segs_per_row) * kSeg;
+        const int y0 = ty * kTileY;
+        const int x = x0 + tid;
+        // stage the weights of rows y0 - v .. y0 + kTileY - 1 + v
+        for (int rr = 0; rr < wrows; ++rr) {
+            const int yy = y0 - v + rr;
+            float a = 0.0f, b = 0.0f;
+            if (yy >= 0 && yy < h && x < w) {
+                const int off = yy * w + x;
+                a = s_lut[dl[off]];
+                b = s_lut[dr[off]];
+            }
+            s_wl[rr * kSeg + tid] = a;
+            s_wr[rr * kSeg + tid] = b;
+        }
+        // stage depth[y][x0 - lo .. x0 + kSeg + bs - lo) for the tile's rows (zeros outside the row)
+        for (int r = 0; r < kTileY; ++r) {
+            const int y = y0 + r;
+            const float* row = base + (int64_t)y * w;
+            for (int i = tid; i < rw; i += kSeg) {
+                const int xx = x0 - lo + i;
+                s_row[r * rw + i] = (y < h && xx >= 0 && xx < w) ? scaled(row[xx], scale) : 0.0f;
+            }
         }
         __syncthreads();
-        const int x = x0 + threadIdx.x;
-        float vl = 0.0f, vr = 0.0f;
-        if (x < w) {
-            float wl, wr;
-            if (v > 0) {
-                wl = 0.0f; wr = 0.0f;
-                const int y0 = max(y - v, 0), y1 = min(y + v, h - 1);
-                for (int yy = y0; yy <= y1; ++yy) {
-                    wl = fmaf(s_lut[dl[(int64_t)yy * w + x]], wv, wl);
-                    wr = fmaf(s_lut[dr[(int64_t)yy * w + x]], wv, wr);
+        float rl[kTileY], rr_[kTileY];
+#pragma unroll
+        for (int r = 0; r < kTileY; ++r) {
+            float vl = 0.0f, vr = 0.0f;
+            const int y = y0 + r;
+            if (y < h && x < w) {
+                float wl, wr;
+                if (v > 0) {
+                    wl = 0.0f; wr = 0.0f;
+                    const float* pl = s_wl + r * kSeg + tid;
+                    const float* pr = s_wr + r * kSeg + tid;
+                    for (int t = 0; t <= 2 * v; ++t) {
+                        wl = fmaf(pl[t * kSeg], wv, wl);
+                        wr = fmaf(pr[t * kSeg], wv, wr);
+                    }
+                } else {
+                    wl = s_wl[r * kSeg + tid];
+                    wr = s_wr[r * kSeg + tid];
                 }
-            } else {
-                wl = s_lut[dl[(int64_t)y * w + x]];
-                wr = s_lut[dr[(int64_t)y * w + x]];
+                const float* prow = s_row + r * rw + tid;
+                float b = 0.0f;
+                for (int k = 0; k < bs; ++k) b = fmaf(prow[k], wb, b);
+                const float d = prow[lo];
+                float t0 = wl * b, t1 = (1.0f - wl) * d;
+                vl = t0 + t1;
+                t0 = wr * b; t1 = (1.0f - wr) * d;
+                vr = t0 + t1;
+                bl[y * w + x] = vl;
+                br[y * w + x] = vr;
+                mnl = fminf(mnl, vl); mxl = fmaxf(mxl, vl);
+                mnr = fminf(mnr, vr); mxr = fmaxf(mxr, vr);
             }
-            float b = 0.0f;
-            for (int k = 0; k < bs; ++k) b = fmaf(s_row[threadIdx.x + k], wb, b);
-            const float d = s_row[threadIdx.x + lo];
-            float t0 = wl * b, t1 = (1.0f - wl) * d;
-            vl = t0 + t1;
-            t0 = wr * b; t1 = (1.0f - wr) * d;
-            vr = t0 + t1;
-            blur_l[((int64_t)frame * h + y) * w + x] = vl;
-            blur_r[((int64_t)frame * h + y) * w + x] = vr;
-            mnl = fminf(mnl, vl); mxl = fmaxf(mxl, vl);
-            mnr = fminf(mnr, vr); mxr = fmaxf(mxr, vr);
+            rl[r] = vl; rr_[r] = vr;
         }
         if (out_l) {  // CPU-technique depth outputs: u8 = trunc(v*255) mod 256, /255, x3 channels (Q1)
-            long long il = (long long)(vl * 255.0f), ir = (long long)(vr * 255.0f);
-            s_vl[threadIdx.x] = (float)(int)(il & 255) / 255.0f;
-            s_vr[threadIdx.x] = (float)(int)(ir & 255) / 255.0f;
+            __syncthreads();   // everyone is done with the weight tiles
+#pragma unroll
+            for (int r = 0; r < kTileY; ++r) {
+                long long il = (long long)(rl[r] * 255.0f), ir = (long long)(rr_[r] * 255.0f);
+                s_vl[r * kSeg + tid] = (float)(int)(il & 255) / 255.0f;
+                s_vr[r * kSeg + tid] = (float)(int)(ir & 255) / 255.0f;
+            }
             __syncthreads();
             const int npx = min(kSeg, w - x0);
-            float* pl = out_l + (((int64_t)frame * h + y) * w + x0) * 3;
-            float* pr = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
-            if (vec_out) {
-                const int nvec = (npx * 3) >> 2;  // npx % 4 == 0 here
-                for (int m = threadIdx.x; m < nvec; m += kSeg) {
-                    int f0 = 4 * m;
-                    float4 a = make_float4(s_vl[f0 / 3], s_vl[(f0 + 1) / 3], s_vl[(f0 + 2) / 3], s_vl[(f0 + 3) / 3]);
-                    float4 c = make_float4(s_vr[f0 / 3], s_vr[(f0 + 1) / 3], s_vr[(f0 + 2) / 3], s_vr[(f0 + 3) / 3]);
-                    st_stream_f4(reinterpret_cast<float4*>(pl) + m, a, pol);
-                    st_stream_f4(reinterpret_cast<float4*>(pr) + m, c, pol);
+            for (int r = 0; r < kTileY; ++r) {
+                const int y = y0 + r;
+                if (y >= h) break;
+                float* pl = out_l + (((int64_t)frame * h + y) * w + x0) * 3;
+                float* pr = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
+                const float* sl = s_vl + r * kSeg;
+                const float* sr = s_vr + r * kSeg;
+                if (vec_out) {
+                    const int nvec = (npx * 3) >> 2;  // npx % 4 == 0 here
+                    for (int m = tid; m < nvec; m += kSeg) {
+                        const int f0 = 4 * m;
+                        const int p0 = f0 / 3, k = f0 - 3 * p0;       // k = 0, 1 or 2 floats of pixel p0 already written
+                        const float a0 = sl[p0], a1 = sl[p0 + 1 < kSeg ? p0 + 1 : p0];
+                        const float c0 = sr[p0], c1 = sr[p0 + 1 < kSeg ? p0 + 1 : p0];
+                        // floats f0..f0+3 belong to pixel p0 for the first (3 - k) of them, then to p0 + 1
+                        float4 a = make_float4(a0, (k < 2) ? a0 : a1, (k < 1) ? a0 : a1, a1);
+                        float4 c = make_float4(c0, (k < 2) ? c0 : c1, (k < 1) ? c0 : c1, c1);
+                        st_stream_f4(reinterpret_cast<float4*>(pl) + m, a, pol);
+                        st_stream_f4(reinterpret_cast<float4*>(pr) + m, c, pol);
+                    }
+                } else {
+                    for (int f = tid; f < npx * 3; f += kSeg) { pl[f] = sl[f / 3]; pr[f] = sr[f / 3]; }
                 }
-            } else {
-                for (int f = threadIdx.x; f < npx * 3; f += kSeg) { pl[f] = s_vl[f / 3]; pr[f] = s_vr[f / 3]; }
             }
         }
         __syncthreads();
     }
     mnl = warp_min(mnl); mxl = warp_max(mxl); mnr = warp_min(mnr); mxr = warp_max(mxr);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = tid >> 5, lane = tid & 31;
     if (lane == 0) { s_red[0][wid] = mnl; s_red[1][wid] = mxl; s_red[2][wid] = mnr; s_red[3][wid] = mxr; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         for (int k = 1; k < kSeg / 32; ++k) {
             mnl = fminf(mnl, s_red[0][k]); mxl = fmaxf(mxl, s_red[1][k]);
             mnr = fminf(mnr, s_red[2][k]); mxr = fmaxf(mxr, s_red[3][k]);
@@ -264,12 +313,15 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     BlurLut lut;
     build_lut(lut, radius, (float)p.blur_falloff);
     const int segs = (w + kSeg - 1) / kSeg;
-    const int items = segs * h;
+    const int tiles_y = (h + kTileY - 1) / kTileY;
+    const int items = segs * tiles_y;
     // few CTAs per frame so the 4 min/max atomics per CTA stay cheap; >= 4 waves in total
-    int per_frame = (148 * 8 * 4 + n - 1) / n;
+    int per_frame = (148 * 5 * 4 + n - 1) / n;
     if (per_frame > items) per_frame = items;
     if (per_frame < 1) per_frame = 1;
-    size_t smem = (size_t)(kSeg + bs + 2 * kSeg) * sizeof(float);
+    size_t smem = ((size_t)2 * (kTileY + 2 * v) * kSeg + (size_t)kTileY * (kSeg + bs)) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_blur_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_begin(K_BLUR_BLEND, s);
     k_blur_blend<<<dim3(per_frame, n), kSeg, smem, s>>>(gray, stats, scale_mode, group < 1 ? 1 : group, n, h,
                                                        w, bs, radius, v, lut, dist_l, dist_r, blur_l,
