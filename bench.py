@@ -44,7 +44,7 @@ BYTES_PER_PX = {"cpu_sbs": 80, "gw_sbs": 76, "anaglyph": 64}  # SURVEY.md 8(d): 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=16, help="frames per GPU per step")
@@ -87,7 +87,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
@@ -216,6 +216,9 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.15)   # every rank: let rank 0's nvidia-smi start, then one more untimed step
+    step()
+    barrier()
     lib.cs_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
