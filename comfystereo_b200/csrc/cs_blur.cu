@@ -88,33 +88,40 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
     }
     __syncthreads();
 
+    // Per 32-pixel word: position of the nearest set bit in an earlier / later word (within reach of the radius),
+    // so that the per-pixel lookup below is loop-free.
     const int far = radius + 1;
+    int* prevpos = reinterpret_cast<int*>(s_bits + 2 * nwords);   // [2][nwords]
+    int* nextpos = prevpos + 2 * nwords;                          // [2][nwords]
+    const int kwords = (radius >> 5) + 1;
+    for (int t = threadIdx.x; t < 2 * nwords; t += blockDim.x) {
+        const int pass = t >= nwords, wi = pass ? t - nwords : t;
+        const uint32_t* bits = pass ? br : bl;
+        int pp = -(1 << 28), np = 1 << 28;
+        for (int k = 1; k <= kwords && wi - k >= 0; ++k) {
+            uint32_t q = bits[wi - k];
+            if (q) { pp = ((wi - k) << 5) + 31 - __clz(q); break; }
+        }
+        for (int k = 1; k <= kwords && wi + k < nwords; ++k) {
+            uint32_t q = bits[wi + k];
+            if (q) { np = ((wi + k) << 5) + __ffs(q) - 1; break; }
+        }
+        prevpos[t] = pp;
+        nextpos[t] = np;
+    }
+    __syncthreads();
     uint8_t* ol = dist_l + ((int64_t)frame * h + y) * w;
     uint8_t* orr = dist_r + ((int64_t)frame * h + y) * w;
     for (int x = threadIdx.x; x < w; x += blockDim.x) {
         const int wi = x >> 5, b = x & 31;
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
-            const uint32_t* bits = pass ? br : bl;
-            int d = far;
-            // nearest set bit at or left of x
-            uint32_t m = bits[wi] & (0xffffffffu >> (31 - b));
-            if (m) d = min(d, b - (31 - __clz(m)));
-            else {
-                for (int k = 1; wi - k >= 0 && (b + 32 * (k - 1) + 1) <= radius; ++k) {
-                    uint32_t q = bits[wi - k];
-                    if (q) { d = min(d, b + 32 * k - (31 - __clz(q))); break; }
-                }
-            }
-            // nearest set bit at or right of x
-            m = bits[wi] & (0xffffffffu << b);
-            if (m) d = min(d, (__ffs(m) - 1) - b);
-            else {
-                for (int k = 1; wi + k < nwords && (32 * (k - 1) + (32 - b)) <= radius; ++k) {
-                    uint32_t q = bits[wi + k];
-                    if (q) { d = min(d, 32 * k - b + (__ffs(q) - 1)); break; }
-                }
-            }
+            const uint32_t word = (pass ? br : bl)[wi];
+            const uint32_t ml = word & (0xffffffffu >> (31 - b));    // bits at or left of x
+            const uint32_t mr = word & (0xffffffffu << b);           // bits at or right of x
+            const int pl = ml ? (wi << 5) + 31 - __clz(ml) : prevpos[pass * nwords + wi];
+            const int pn = mr ? (wi << 5) + __ffs(mr) - 1 : nextpos[pass * nwords + wi];
+            const int d = min(min(x - pl, pn - x), far);
             (pass ? orr : ol)[x] = (uint8_t)d;
         }
     }
@@ -123,24 +130,30 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
 // ------------------------------------------------------------------------------------ blend
 constexpr int kSeg = 256;  // pixels per row segment = threads per CTA
 constexpr int kTileY = 8;  // rows per work item
+constexpr int kRowPad = 16;
 
-// Work item = kTileY rows x kSeg columns.  The LUT weights of the kTileY + 2v rows the vertical box touches and
-// the kTileY depth row segments (with the horizontal box's halo) are staged in shared memory once, so every tap
-// of both boxes is one LDS + one FFMA.  Rows outside the image hold weight 0: fmaf(0, wv, acc) == acc, which is
-// the reference's zero padding.  Tap order (ascending, fmaf) is the oracle's.
+// Work item = kTileY rows x kSeg columns, staged once in shared memory: the LUT weights of the kTileY + 2v rows the
+// vertical box touches, and the kTileY depth row segments with the horizontal box's halo.
+//   pass 1  thread = column: one walk down the staged weight rows feeds all kTileY vertical sums (each weight is
+//           loaded once and used by up to 2v+1 accumulators; every accumulator still sees its taps in ascending order)
+//   pass 2  thread = (row, 8 consecutive columns): the bs-tap horizontal box for 8 pixels from a register window
+//           (15 loads per 64 fused multiply-adds), blend, min/max, depth outputs
+// Rows outside the image hold weight 0: fmaf(0, wv, acc) == acc, which is the reference's zero padding.
+// Tap order (ascending, fmaf) is the oracle's, so the result is bit-identical to it.
+template <int V>   // vertical smoothing radius (0..15): compile-time so that the column walk unrolls without predicates
 __global__ void __launch_bounds__(kSeg) k_blur_blend(
     const float* __restrict__ gray, FrameStats* __restrict__ st, int scale_mode, int group, int n,
-    int h, int w, int bs, int radius, int v, const __grid_constant__ BlurLut lut,
+    int h, int w, int bs, int radius, const __grid_constant__ BlurLut lut,
     const uint8_t* __restrict__ dist_l, const uint8_t* __restrict__ dist_r, float* __restrict__ blur_l,
     float* __restrict__ blur_r, float* __restrict__ out_l, float* __restrict__ out_r, int items_per_frame,
     int segs_per_row) {
-    extern __shared__ float s_dyn[];
-    const int wrows = kTileY + 2 * v;
-    float* s_wl = s_dyn;                         // [wrows][kSeg]
+    extern __shared__ __align__(16) float s_dyn[];
+    constexpr int v = V;
+    constexpr int wrows = kTileY + 2 * V;
+    const int rw = (kSeg + bs + kRowPad + 3) & ~3;     // row pitch, multiple of 4 floats
+    float* s_wl = s_dyn;                         // [wrows][kSeg]   later: [kTileY][kSeg] vertical sums, then outputs
     float* s_wr = s_wl + wrows * kSeg;           // [wrows][kSeg]
-    float* s_row = s_wr + wrows * kSeg;          // [kTileY][kSeg + bs]
-    float* s_vl = s_wl;                          // output staging reuses the weight tiles: [kTileY][kSeg] x 2
-    float* s_vr = s_wl + kTileY * kSeg;
+    float* s_row = s_wr + wrows * kSeg;          // [kTileY][rw]
     __shared__ float s_red[4][kSeg / 32];
     __shared__ float s_lut[256];
     const int tid = threadIdx.x;
@@ -150,7 +163,6 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
     const float wv = 1.0f / (float)(2 * v + 1);
     const float wb = 1.0f / (float)bs;
     const int lo = bs / 2;
-    const int rw = kSeg + bs;
     const uint64_t pol = policy_evict_first();
     const float* base = gray + (int64_t)frame * h * w;
     const uint8_t* dl = dist_l + (int64_t)frame * h * w;
@@ -158,6 +170,8 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
     float* bl = blur_l + (int64_t)frame * h * w;
     float* br = blur_r + (int64_t)frame * h * w;
     const bool vec_out = out_l && (w % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0);
+    const bool vec_blur = (w % 4 == 0) && ((uintptr_t)blur_l % 16 == 0) && ((uintptr_t)blur_r % 16 == 0);
+    const int pr = tid >> 5, pg = tid & 31;      // pass 2: row of the tile, group of 8 columns
     __syncthreads();
 
     float mnl = INFINITY, mxl = -INFINITY, mnr = INFINITY, mxr = -INFINITY;
@@ -165,94 +179,146 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
         const int ty = item / segs_per_row, x0 = (item - ty * segs_per_row) * kSeg;
         const int y0 = ty * kTileY;
         const int x = x0 + tid;
-        // stage the weights of rows y0 - v .. y0 + kTileY - 1 + v
-        for (int rr = 0; rr < wrows; ++rr) {
-            const int yy = y0 - v + rr;
-            float a = 0.0f, b = 0.0f;
-            if (yy >= 0 && yy < h && x < w) {
-                const int off = yy * w + x;
-                a = s_lut[dl[off]];
-                b = s_lut[dr[off]];
-            }
-            s_wl[rr * kSeg + tid] = a;
-            s_wr[rr * kSeg + tid] = b;
-        }
-        // stage depth[y][x0 - lo .. x0 + kSeg + bs - lo) for the tile's rows (zeros outside the row)
-        for (int r = 0; r < kTileY; ++r) {
-            const int y = y0 + r;
-            const float* row = base + (int64_t)y * w;
-            for (int i = tid; i < rw; i += kSeg) {
-                const int xx = x0 - lo + i;
-                s_row[r * rw + i] = (y < h && xx >= 0 && xx < w) ? scaled(row[xx], scale) : 0.0f;
-            }
-        }
-        __syncthreads();
-        float rl[kTileY], rr_[kTileY];
+        // ---- stage the weights of rows y0 - v .. y0 + kTileY - 1 + v (all byte loads first, then the LUT gathers)
+        {
+            uint32_t da[wrows], db[wrows];
+            const bool xin = x < w;
 #pragma unroll
-        for (int r = 0; r < kTileY; ++r) {
-            float vl = 0.0f, vr = 0.0f;
-            const int y = y0 + r;
-            if (y < h && x < w) {
-                float wl, wr;
-                if (v > 0) {
-                    wl = 0.0f; wr = 0.0f;
-                    const float* pl = s_wl + r * kSeg + tid;
-                    const float* pr = s_wr + r * kSeg + tid;
-                    for (int t = 0; t <= 2 * v; ++t) {
-                        wl = fmaf(pl[t * kSeg], wv, wl);
-                        wr = fmaf(pr[t * kSeg], wv, wr);
-                    }
-                } else {
-                    wl = s_wl[r * kSeg + tid];
-                    wr = s_wr[r * kSeg + tid];
-                }
-                const float* prow = s_row + r * rw + tid;
-                float b = 0.0f;
-                for (int k = 0; k < bs; ++k) b = fmaf(prow[k], wb, b);
-                const float d = prow[lo];
-                float t0 = wl * b, t1 = (1.0f - wl) * d;
-                vl = t0 + t1;
-                t0 = wr * b; t1 = (1.0f - wr) * d;
-                vr = t0 + t1;
-                bl[y * w + x] = vl;
-                br[y * w + x] = vr;
-                mnl = fminf(mnl, vl); mxl = fmaxf(mxl, vl);
-                mnr = fminf(mnr, vr); mxr = fmaxf(mxr, vr);
+            for (int rr = 0; rr < wrows; ++rr) {
+                const int yy = y0 - v + rr;
+                const bool in = xin && yy >= 0 && yy < h;
+                const int off = in ? yy * w + x : 0;
+                da[rr] = in ? (uint32_t)dl[off] : 256u;
+                db[rr] = in ? (uint32_t)dr[off] : 256u;
             }
-            rl[r] = vl; rr_[r] = vr;
+#pragma unroll
+            for (int rr = 0; rr < wrows; ++rr) {
+                s_wl[rr * kSeg + tid] = (da[rr] < 256u) ? s_lut[da[rr]] : 0.0f;
+                s_wr[rr * kSeg + tid] = (db[rr] < 256u) ? s_lut[db[rr]] : 0.0f;
+            }
         }
-        if (out_l) {  // CPU-technique depth outputs: u8 = trunc(v*255) mod 256, /255, x3 channels (Q1)
-            __syncthreads();   // everyone is done with the weight tiles
+        // ---- stage depth[y][x0 - lo .. ) for the tile's rows (zeros outside the row)
+        for (int i = tid; i < rw; i += kSeg) {
+            const int xx = x0 - lo + i;
+            const bool xin2 = xx >= 0 && xx < w;
+            float tmp[kTileY];
 #pragma unroll
             for (int r = 0; r < kTileY; ++r) {
-                long long il = (long long)(rl[r] * 255.0f), ir = (long long)(rr_[r] * 255.0f);
-                s_vl[r * kSeg + tid] = (float)(int)(il & 255) / 255.0f;
-                s_vr[r * kSeg + tid] = (float)(int)(ir & 255) / 255.0f;
+                const int y = y0 + r;
+                tmp[r] = (xin2 && y < h) ? base[(int64_t)y * w + xx] : 0.0f;
             }
+#pragma unroll
+            for (int r = 0; r < kTileY; ++r) s_row[r * rw + i] = scaled(tmp[r], scale);
+        }
+        __syncthreads();
+        // ---- pass 1: vertical sums of column tid for all kTileY rows
+        float al[kTileY], ar[kTileY];
+        if (v > 0) {
+#pragma unroll
+            for (int r = 0; r < kTileY; ++r) { al[r] = 0.0f; ar[r] = 0.0f; }
+#pragma unroll
+            for (int t = 0; t < wrows; ++t) {
+                const float a = s_wl[t * kSeg + tid], b = s_wr[t * kSeg + tid];
+#pragma unroll
+                for (int r = 0; r < kTileY; ++r) {
+                    const int tap = t - r;
+                    if (tap >= 0 && tap <= 2 * v) { al[r] = fmaf(a, wv, al[r]); ar[r] = fmaf(b, wv, ar[r]); }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kTileY; ++r) { al[r] = s_wl[r * kSeg + tid]; ar[r] = s_wr[r * kSeg + tid]; }
+        }
+        __syncthreads();   // all reads of the weight tiles are done
+#pragma unroll
+        for (int r = 0; r < kTileY; ++r) { s_wl[r * kSeg + tid] = al[r]; s_wr[r * kSeg + tid] = ar[r]; }
+        __syncthreads();
+        // ---- pass 2: horizontal box for 8 consecutive pixels of row pr
+        {
+            const int y = y0 + pr;
+            const int c0 = pg * 8;
+            const float* prow = s_row + pr * rw + c0;
+            float bsum[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[j] = 0.0f;
+            for (int k0 = 0; k0 < bs; k0 += 8) {
+                float win[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(prow + k0 + 4 * q);
+                    win[4 * q] = t4.x; win[4 * q + 1] = t4.y; win[4 * q + 2] = t4.z; win[4 * q + 3] = t4.w;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    if (k0 + kk < bs) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bsum[j] = fmaf(win[j + kk], wb, bsum[j]);
+                    }
+                }
+            }
+            float vl[8], vr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = prow[lo + j];
+                const float wl = s_wl[pr * kSeg + c0 + j], wr = s_wr[pr * kSeg + c0 + j];
+                float t0 = wl * bsum[j], t1 = (1.0f - wl) * d;
+                vl[j] = t0 + t1;
+                t0 = wr * bsum[j]; t1 = (1.0f - wr) * d;
+                vr[j] = t0 + t1;
+            }
+            const int xg = x0 + c0;
+            if (y < h) {
+                if (vec_blur && xg + 8 <= w) {
+                    float4* pl4 = reinterpret_cast<float4*>(bl + (int64_t)y * w + xg);
+                    float4* pr4 = reinterpret_cast<float4*>(br + (int64_t)y * w + xg);
+                    pl4[0] = make_float4(vl[0], vl[1], vl[2], vl[3]); pl4[1] = make_float4(vl[4], vl[5], vl[6], vl[7]);
+                    pr4[0] = make_float4(vr[0], vr[1], vr[2], vr[3]); pr4[1] = make_float4(vr[4], vr[5], vr[6], vr[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (xg + j < w) { bl[(int64_t)y * w + xg + j] = vl[j]; br[(int64_t)y * w + xg + j] = vr[j]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (xg + j < w) {
+                        mnl = fminf(mnl, vl[j]); mxl = fmaxf(mxl, vl[j]);
+                        mnr = fminf(mnr, vr[j]); mxr = fmaxf(mxr, vr[j]);
+                    }
+            }
+            if (out_l) {  // CPU-technique depth outputs: u8 = trunc(v*255) mod 256, /255 (Q1); staged in place
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    long long il = (long long)(vl[j] * 255.0f), ir = (long long)(vr[j] * 255.0f);
+                    s_wl[pr * kSeg + c0 + j] = (float)(int)(il & 255) / 255.0f;
+                    s_wr[pr * kSeg + c0 + j] = (float)(int)(ir & 255) / 255.0f;
+                }
+            }
+        }
+        if (out_l) {
             __syncthreads();
             const int npx = min(kSeg, w - x0);
             for (int r = 0; r < kTileY; ++r) {
                 const int y = y0 + r;
                 if (y >= h) break;
                 float* pl = out_l + (((int64_t)frame * h + y) * w + x0) * 3;
-                float* pr = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
-                const float* sl = s_vl + r * kSeg;
-                const float* sr = s_vr + r * kSeg;
+                float* pr_ = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
+                const float* sl = s_wl + r * kSeg;
+                const float* sr = s_wr + r * kSeg;
                 if (vec_out) {
                     const int nvec = (npx * 3) >> 2;  // npx % 4 == 0 here
                     for (int m = tid; m < nvec; m += kSeg) {
                         const int f0 = 4 * m;
-                        const int p0 = f0 / 3, k = f0 - 3 * p0;       // k = 0, 1 or 2 floats of pixel p0 already written
-                        const float a0 = sl[p0], a1 = sl[p0 + 1 < kSeg ? p0 + 1 : p0];
-                        const float c0 = sr[p0], c1 = sr[p0 + 1 < kSeg ? p0 + 1 : p0];
+                        const int p0 = f0 / 3, k = f0 - 3 * p0;       // float f0 is channel k of pixel p0
+                        const int p1 = p0 + 1 < kSeg ? p0 + 1 : p0;
+                        const float a0 = sl[p0], a1 = sl[p1], c0 = sr[p0], c1 = sr[p1];
                         // floats f0..f0+3 belong to pixel p0 for the first (3 - k) of them, then to p0 + 1
                         float4 a = make_float4(a0, (k < 2) ? a0 : a1, (k < 1) ? a0 : a1, a1);
                         float4 c = make_float4(c0, (k < 2) ? c0 : c1, (k < 1) ? c0 : c1, c1);
                         st_stream_f4(reinterpret_cast<float4*>(pl) + m, a, pol);
-                        st_stream_f4(reinterpret_cast<float4*>(pr) + m, c, pol);
+                        st_stream_f4(reinterpret_cast<float4*>(pr_) + m, c, pol);
                     }
                 } else {
-                    for (int f = tid; f < npx * 3; f += kSeg) { pl[f] = sl[f / 3]; pr[f] = sr[f / 3]; }
+                    for (int f = tid; f < npx * 3; f += kSeg) { pl[f] = sl[f / 3]; pr_[f] = sr[f / 3]; }
                 }
             }
         }
@@ -276,6 +342,33 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
 
 // weight(dist) = clamp(1 - dist/R, 0, 1) ** falloff, float32 (SIG:1168).  Built on the host once
 // per call (<= 256 entries): torch.pow special-cases exponents 1, 2, 3, 0.5; otherwise powf.
+template <int V, typename... Args>
+static void launch_blend_one(dim3 grid, size_t smem, cudaStream_t s, Args... args) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_blur_blend<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_blur_blend<V><<<grid, kSeg, smem, s>>>(args...);
+}
+template <typename... Args>
+static void launch_blend_v(int v, dim3 grid, size_t smem, cudaStream_t s, Args... args) {
+    switch (v) {
+        case 0: launch_blend_one<0>(grid, smem, s, args...); break;
+        case 1: launch_blend_one<1>(grid, smem, s, args...); break;
+        case 2: launch_blend_one<2>(grid, smem, s, args...); break;
+        case 3: launch_blend_one<3>(grid, smem, s, args...); break;
+        case 4: launch_blend_one<4>(grid, smem, s, args...); break;
+        case 5: launch_blend_one<5>(grid, smem, s, args...); break;
+        case 6: launch_blend_one<6>(grid, smem, s, args...); break;
+        case 7: launch_blend_one<7>(grid, smem, s, args...); break;
+        case 8: launch_blend_one<8>(grid, smem, s, args...); break;
+        case 9: launch_blend_one<9>(grid, smem, s, args...); break;
+        case 10: launch_blend_one<10>(grid, smem, s, args...); break;
+        case 11: launch_blend_one<11>(grid, smem, s, args...); break;
+        case 12: launch_blend_one<12>(grid, smem, s, args...); break;
+        case 13: launch_blend_one<13>(grid, smem, s, args...); break;
+        case 14: launch_blend_one<14>(grid, smem, s, args...); break;
+        default: launch_blend_one<15>(grid, smem, s, args...); break;
+    }
+}
+
 static void build_lut(BlurLut& lut, int radius, float falloff) {
     for (int k = 0; k < 256; ++k) {
         float q = (float)k / (float)radius;   // radius 0 -> NaN at k = 0, inf elsewhere (quirk Q11)
@@ -297,13 +390,13 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
                         int w, const cs_params& p, float* blur_l, float* blur_r, uint8_t* dist,
                         float* depth_l_out, float* depth_r_out, cudaStream_t s) {
     const int bs = p.blur_box, radius = p.blur_radius, v = p.blur_vert_smooth;
-    if (bs < 1 || radius < 0 || radius > kMaxBlurRadius || v < 0) return cudaErrorInvalidValue;
+    if (bs < 1 || radius < 0 || radius > kMaxBlurRadius || v < 0 || v > 15) return cudaErrorInvalidValue;
     uint8_t* dist_l = dist;
     uint8_t* dist_r = dist + (int64_t)n * h * w;
     const float edge_div = (float)(10.0 * p.blur_edge_threshold);  // python float 10*thr -> float32 scalar
     const int nwords = (w + 31) >> 5;
     prof_begin(K_EDGE_DIST, s);
-    k_edge_dist<<<dim3(h, n), 256, 2 * nwords * sizeof(uint32_t), s>>>(
+    k_edge_dist<<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
         gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
     prof_end(K_EDGE_DIST, s);
     count_launch();
@@ -319,13 +412,12 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     int per_frame = (148 * 5 * 4 + n - 1) / n;
     if (per_frame > items) per_frame = items;
     if (per_frame < 1) per_frame = 1;
-    size_t smem = ((size_t)2 * (kTileY + 2 * v) * kSeg + (size_t)kTileY * (kSeg + bs)) * sizeof(float);
+    const int rw = (kSeg + bs + kRowPad + 3) & ~3;
+    size_t smem = ((size_t)2 * (kTileY + 2 * v) * kSeg + (size_t)kTileY * rw) * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_blur_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_begin(K_BLUR_BLEND, s);
-    k_blur_blend<<<dim3(per_frame, n), kSeg, smem, s>>>(gray, stats, scale_mode, group < 1 ? 1 : group, n, h,
-                                                       w, bs, radius, v, lut, dist_l, dist_r, blur_l,
-                                                       blur_r, depth_l_out, depth_r_out, items, segs);
+    launch_blend_v(v, dim3(per_frame, n), smem, s, gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, bs, radius, lut,
+                   dist_l, dist_r, blur_l, blur_r, depth_l_out, depth_r_out, items, segs);
     prof_end(K_BLUR_BLEND, s);
     count_launch();
     return cudaGetLastError();

@@ -760,7 +760,10 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     uint32_t* out = a.out[eye] + row_off;
     bool give_up = false;
     const bool shp = c.sharp;
-    for (int col = tid; col < w; col += kPolyThreads) {
+    // every warp owns an equal, contiguous share of the row, so all 16 warps stay busy until the end of the sweep
+    const int cols_per_warp = (w + (kPolyThreads / 32) - 1) / (kPolyThreads / 32);
+    const int wbeg = wid * cols_per_warp, wend = min(wbeg + cols_per_warp, w);
+    for (int col = wbeg + lane; col < wend; col += 32) {
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;   // float32-valued accumulators kept in float64 registers
         const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;
         const double cold = u8_to_f64((uint32_t)col), col1d = cold + 1.0;
