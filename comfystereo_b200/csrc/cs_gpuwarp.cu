@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
     float* src = dest + w;
     float* zb = src + w;
     int* win = reinterpret_cast<int*>(zb + w);
-    uint32_t* fbits = reinterpret_cast<uint32_t*>(win + w);   // filled (src >= 0) bitmap
+    uint32_t* fbits = reinterpret_cast<uint32_t*>(win + w + 16);   // filled (src >= 0) bitmap
     uint32_t* ubits = fbits + nwords;                         // unfilled in either eye (mask)
     __shared__ int s_last;
 
@@ -136,41 +136,58 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
             float p = m + sep_px;
             po[x] = p;
             dest[x] = (float)x + p;
-            src[x] = -1.0f;
-            zb[x] = -1.0f;
         }
         __syncthreads();
 
-        for (int k = 0; k < 8; ++k) {
-            for (int x = threadIdx.x; x < w; x += blockDim.x) win[x] = -1;
-            __syncthreads();
-            for (int i = threadIdx.x; i + 1 < w; i += blockDim.x) {
-                float dm = fminf(dest[i], dest[i + 1]);
-                float fl = floorf(dm);
-                // clamp in float first: the column index only matters after clamping to [0, w-1]
-                long long c = (long long)fl + k;
-                int cs = c < 0 ? 0 : (c > w - 1 ? w - 1 : (int)c);
-                atomicMax(&win[cs], i);
-            }
-            __syncthreads();
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
-                int i = win[x];
-                if (i < 0) continue;
-                float dl = dest[i], dr = dest[i + 1];
-                bool connected = fabsf(po[i + 1] - po[i]) < 1.5f;
-                float dm = fminf(dl, dr);
-                long long c = (long long)floorf(dm) + k;
-                float sw = dr - dl;
-                float safe = (fabsf(sw) < 1e-4f) ? 1.0f : sw;
-                float frac = ((float)c - dl) / safe;
-                bool valid = connected && c >= 0 && c < w && frac >= 0.0f && frac < 1.0f;
-                if (!valid) continue;
-                float a0 = ndv[i] * (1.0f - frac), a1 = ndv[i + 1] * frac;
-                float zi = a0 + a1;
-                if (zi > zb[x] + 1e-6f) { zb[x] = zi; src[x] = (float)i + frac; }
-            }
-            __syncthreads();
+        // The 8 scatter rounds.  In round k pair i targets column clamp(cb_i + k), cb_i = floor(min(dest_i, dest_i+1)),
+        // and only the highest-index pair targeting a column decides it (Q8).  So one pass builds
+        //     M[c] = max { i : cb_i == c }        (cb clamped into [-8, w+7]),
+        // and the decisive pair of column x in round k is M[x - k] (for the two border columns, the maximum over
+        // everything the clamp folds onto them).  A pair can only be VALID (0 <= frac < 1) while its column stays
+        // inside [dest_i, dest_i+1), which is shorter than 2.5 for connected pairs: rounds k >= 4 never change
+        // anything (an invalid decisive pair writes back the value it read), so rounds 0..4 reproduce all 8.
+        int* M = win;   // [w + 16], index c + 8
+        for (int x = threadIdx.x; x < w + 16; x += blockDim.x) M[x] = -1;
+        __syncthreads();
+        for (int i = threadIdx.x; i + 1 < w; i += blockDim.x) {
+            const float fl = floorf(fminf(dest[i], dest[i + 1]));
+            const int cbc = (fl < -8.0f) ? -8 : ((fl > (float)(w + 7)) ? w + 7 : (int)fl);
+            atomicMax(&M[cbc + 8], i);
         }
+        __syncthreads();
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            float z = -1.0f, sv = -1.0f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int i;
+                if (x == 0) {
+                    i = -1;
+                    for (int c = -8; c <= -k; ++c) i = max(i, M[c + 8]);
+                    if (w == 1) i = -1;
+                } else if (x == w - 1) {
+                    i = -1;
+                    for (int c = w - 1 - k; c <= w + 7; ++c) i = max(i, M[c + 8]);
+                } else {
+                    i = M[x - k + 8];
+                }
+                if (i < 0) continue;
+                const float dl = dest[i], dr = dest[i + 1];
+                const bool connected = fabsf(po[i + 1] - po[i]) < 1.5f;
+                const float dm = fminf(dl, dr);
+                const long long c = (long long)floorf(dm) + k;
+                const float sw = dr - dl;
+                const float safe = (fabsf(sw) < 1e-4f) ? 1.0f : sw;
+                const float frac = ((float)c - dl) / safe;
+                const bool valid = connected && c >= 0 && c < w && frac >= 0.0f && frac < 1.0f;
+                if (!valid) continue;
+                const float a0 = ndv[i] * (1.0f - frac), a1 = ndv[i + 1] * frac;
+                const float zi = a0 + a1;
+                if (zi > z + 1e-6f) { z = zi; sv = (float)i + frac; }
+            }
+            zb[x] = z;
+            src[x] = sv;
+        }
+        __syncthreads();
 
         // filled bitmap, row-wide right-most filled column (SIG:404-410 quirk), unfilled mask
         if (threadIdx.x == 0) s_last = -1;
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
 
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
-    size_t smem = (size_t)a.w * 24 + (size_t)nwords * 8;
+    size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_gpuwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
