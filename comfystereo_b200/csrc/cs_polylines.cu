@@ -648,7 +648,8 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     // ---- D: reach = prefix max over sorted segments of their end x1; bucket starts
     {
         float m = -INFINITY;
-        float loc[PER];
+        float loc[PER], avv[PER], x1v[PER];
+        int spv[PER];
         int bprev;
         {
             int kp = i0 - 1;
@@ -660,15 +661,19 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
         for (int e = 0; e < PER; ++e) {
             const int k = i0 + e;
             float x1 = -INFINITY;
+            avv[e] = 0.0f; spv[e] = 0;
             if (k < npts) {
                 const int sp = (int)(info[k] & 0xFFFFu);
                 if (k < nsg) x1 = px[sp + 1];
-                float fx = floorf(px[sp]);
+                const float pv = px[sp];
+                avv[e] = pv; spv[e] = sp;
+                float fx = floorf(pv);
                 int b = (fx < 0.0f) ? 0 : ((fx >= (float)w) ? w + 1 : (int)fx + 1);
                 for (int q = bprev + 1; q <= b; ++q) start[q] = k;
                 bprev = b;
                 if (k == npts - 1) start[w + 2] = npts;
             }
+            x1v[e] = x1;
             m = fmaxf(m, x1);
             loc[e] = m;
         }
@@ -687,43 +692,43 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
         for (int q = 0; q < PER / 4; ++q)
             reinterpret_cast<float4*>(reach + i0)[q] = make_float4(fmaxf(loc[4 * q], em), fmaxf(loc[4 * q + 1], em),
                                                                    fmaxf(loc[4 * q + 2], em), fmaxf(loc[4 * q + 3], em));
+        // ---- D2 (first half): an interval whose left point no EARLIER segment reaches past has exactly its own
+        // segment as candidate (or none, if that one does not go forward).  Everything else goes to a work list.
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int k = i0 + e;
+            if (k >= nsg) continue;
+            const float rprev = (e == 0) ? em : fmaxf(loc[e - 1], em);   // reach[k - 1]
+            if (rprev > avv[e]) {
+                tlist[atomicAdd(&s_ntwo, 1)] = (unsigned short)k;
+            } else {
+                const uint32_t code = (x1v[e] > avv[e]) ? 1u : 0u;
+                info[k] = (uint32_t)spv[e] | (code << kCodeShift);
+            }
+        }
     }
     __syncthreads();
 
-    // ---- D2: active set of every sorted interval (a, b) = (point k, point k+1).  For a centre strictly inside, a
-    // segment j is active iff it starts at or before a (j <= k) and ends beyond a; nothing between a and b is a point,
-    // so all of this is float32 comparisons.  Intervals with up to two active segments are encoded in info[k].
-#pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const int k = i0 + e;
-        if (k >= nsg) continue;
-        const uint32_t me = info[k] & 0xFFFFu;
-        const float av = px[me];
-        int cnt = 0, o1 = 0, o2 = 0;
-        for (int j = k; j >= 0 && reach[j] > av; --j) {
-            const int sp = (int)(info[j] & 0xFFFFu);
-            if (px[sp + 1] > av) {
-                if (cnt == 0) o1 = k - j; else if (cnt == 1) o2 = k - j;
-                ++cnt;
-            }
-        }
-        uint32_t code = (uint32_t)min(cnt, 3);
-        if (o1 > 127 || o2 > 127) code = 3u;
-        if (code == 2u) tlist[atomicAdd(&s_ntwo, 1)] = (unsigned short)k;   // resolved below by the whole CTA
-        info[k] = me | (code << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
-    }
-    __syncthreads();
+    // ---- D2 (second half): active set of the listed intervals (a, b) = (point k, point k+1).  For a centre strictly
+    // inside, a segment j is active iff it starts at or before a (j <= k) and ends beyond a; nothing between a and b
+    // is a point, so all of this is float32 comparisons.  Up to two active segments are encoded in info[k].
     {
-        const int ntwo = s_ntwo;
-        for (int q = tid; q < ntwo; q += kPolyThreads) {
+        const int nlist = s_ntwo;
+        for (int q = tid; q < nlist; q += kPolyThreads) {
             const int k = tlist[q];
-            const uint32_t inf = info[k];
-            const uint32_t me = inf & 0xFFFFu;
-            int o1 = (int)((inf >> kOff1Shift) & 127u);
-            const int o2 = (int)((inf >> kOff2Shift) & 127u);
+            const uint32_t me = info[k] & 0xFFFFu;
             const float av = px[me];
-            uint32_t code = 2u;
-            {
+            int cnt = 0, o1 = 0, o2 = 0;
+            for (int j = k; j >= 0 && reach[j] > av; --j) {
+                const int sp = (int)(info[j] & 0xFFFFu);
+                if (px[sp + 1] > av) {
+                    if (cnt == 0) o1 = k - j; else if (cnt == 1) o2 = k - j;
+                    ++cnt;
+                }
+            }
+            uint32_t code = (uint32_t)min(cnt, 3);
+            if (o1 > 127 || o2 > 127) code = 3u;
+            if (code == 2u) {
                 // Interpolated closeness is linear in the centre, so if one candidate leads at both ends of the interval
                 // by more than any rounding could matter, it leads at every centre inside: the interval becomes a
                 // one-candidate interval.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
@@ -748,8 +753,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 if (safe && a_lo > b_lo + margin && a_hi > b_hi + margin) code = 1u;                     // first candidate
                 else if (safe && b_lo > a_lo + margin && b_hi > a_hi + margin) { code = 1u; o1 = o2; }  // second candidate
             }
-            if (code == 1u)
-                info[k] = me | (1u << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
+            info[k] = me | (code << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
         }
     }
     __syncthreads();
