@@ -508,8 +508,8 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));  // [w]
     unsigned short* tlist = reinterpret_cast<unsigned short*>(simg + w);  // [NP] sorted intervals with two active segments
     __shared__ float s_wa[16], s_wb[16];
-    __shared__ int s_flag, s_ndirty, s_ntwo;
-    if (tid == 0) { s_flag = 0; s_ndirty = 0; s_ntwo = 0; }
+    __shared__ int s_flag, s_ndirty, s_ntwo, s_next;
+    if (tid == 0) { s_flag = 0; s_ndirty = 0; s_ntwo = 0; s_next = 0; }
     // during the sort the reach[] region holds the list of out-of-order points and their ranks (uint16 each)
     unsigned short* dlist = reinterpret_cast<unsigned short*>(reach);
     unsigned short* drank = dlist + NP;
@@ -694,17 +694,24 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                                                                    fmaxf(loc[4 * q + 2], em), fmaxf(loc[4 * q + 3], em));
         // ---- D2 (first half): an interval whose left point no EARLIER segment reaches past has exactly its own
         // segment as candidate (or none, if that one does not go forward).  Everything else goes to a work list.
+        uint32_t hard = 0;
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
             const int k = i0 + e;
             if (k >= nsg) continue;
             const float rprev = (e == 0) ? em : fmaxf(loc[e - 1], em);   // reach[k - 1]
             if (rprev > avv[e]) {
-                tlist[atomicAdd(&s_ntwo, 1)] = (unsigned short)k;
+                hard |= 1u << e;
             } else {
                 const uint32_t code = (x1v[e] > avv[e]) ? 1u : 0u;
                 info[k] = (uint32_t)spv[e] | (code << kCodeShift);
             }
+        }
+        if (hard) {
+            int base = atomicAdd(&s_ntwo, __popc(hard));
+#pragma unroll
+            for (int e = 0; e < PER; ++e)
+                if (hard & (1u << e)) tlist[base++] = (unsigned short)(i0 + e);
         }
     }
     __syncthreads();
@@ -764,10 +771,15 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     uint32_t* out = a.out[eye] + row_off;
     bool give_up = false;
     const bool shp = c.sharp;
-    // every warp owns an equal, contiguous share of the row, so all 16 warps stay busy until the end of the sweep
-    const int cols_per_warp = (w + (kPolyThreads / 32) - 1) / (kPolyThreads / 32);
-    const int wbeg = wid * cols_per_warp, wend = min(wbeg + cols_per_warp, w);
-    for (int col = wbeg + lane; col < wend; col += 32) {
+    // warps take 32-column blocks from a shared counter: blocks inside folds cost several times more than smooth ones
+    const int nblk = (w + 31) >> 5;
+    for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(&s_next, 1);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        if (blk >= nblk) break;
+        const int col = (blk << 5) + lane;
+        if (col >= w) continue;
         double c0 = 0.5, c1 = 0.5, c2 = 0.5;   // float32-valued accumulators kept in float64 registers
         const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;
         const double cold = u8_to_f64((uint32_t)col), col1d = cold + 1.0;
