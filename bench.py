@@ -259,6 +259,12 @@ def main():
     timed = {k: v for k, v in kernels.items() if k != "misc"}
     total_k_ms = sum(v[0] for v in timed.values()) or 1.0
     dom = max(timed, key=lambda k: timed[k][0]) if timed else None
+    traffic_px = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic_px = json.load(f)["dram_bytes_per_input_pixel"]   # dram read+write per input pixel, from an ncu capture
+    except Exception:  # noqa: BLE001
+        pass
     roofline = None
     if dom:
         d_ms, d_n = timed[dom]
@@ -266,7 +272,11 @@ def main():
         per_launch_bytes = k_bytes_px.get(dom, 24) * units_px
         achieved = per_launch_bytes / (d_ms / d_n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak,
+                    "traffic": (traffic_px[dom] * units_px) if dom in traffic_px else None,
+                    "traffic_source": "profiles/ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, "
+                                      "scaled to the pixels of one launch)" if dom in traffic_px else None,
+                    "peak_source": peak_src,
                     "bytes_per_launch": per_launch_bytes, "ms_per_launch": d_ms / d_n,
                     "share_of_step": d_ms / total_k_ms,
                     "path": {"bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
