@@ -15,7 +15,7 @@ ERRORS = {-1: "CS_ERR_ARG", -2: "CS_ERR_CUDA", -3: "CS_ERR_DEVICE", -4: "CS_ERR_
           -5: "CS_ERR_UNSUPPORTED", -6: "CS_ERR_MODE"}
 
 FILL_KEYS = ["none", "naive", "naive_interpolating", "polylines_soft", "polylines_sharp", "inverse",
-             "hybrid_edge", "gpu_warp"]                      # index = cs_fill
+             "hybrid_edge", "gpu_warp", "none_post", "inverse_post", "hybrid_edge_plus"]   # index = cs_fill
 MODES = ["left-right", "right-left", "top-bottom", "bottom-top", "red-cyan-anaglyph", "left-only",
          "only-right", "cyan-red-reverseanaglyph"]           # index = cs_mode
 

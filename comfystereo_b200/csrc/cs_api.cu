@@ -54,11 +54,13 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
-static bool is_cpu_technique(int fill) { return fill >= CS_FILL_NONE && fill <= CS_FILL_HYBRID_EDGE; }
+static bool is_cpu_technique(int fill) {
+    return (fill >= CS_FILL_NONE && fill <= CS_FILL_HYBRID_EDGE) || (fill >= CS_FILL_NONE_POST && fill <= CS_FILL_HYBRID_EDGE_PLUS);
+}
 
 static int check_params(const cs_params* p) {
     if (!p) return fail(CS_ERR_ARG, "params is NULL");
-    if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_GPU_WARP) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
+    if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_HYBRID_EDGE_PLUS) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
     if (p->mode < CS_MODE_LEFT_RIGHT || p->mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
     if (p->blur_enabled) {
         if (p->blur_box < 1) return fail(CS_ERR_UNSUPPORTED, "kernel size should be greater than zero");
@@ -126,6 +128,9 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
         if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP) {
             ws.warp_scratch_bytes = polylines_scratch_bytes(chunk, h);
             ws.warp_scratch = take(ws.warp_scratch_bytes);
+        } else if (p->fill == CS_FILL_HYBRID_EDGE_PLUS) {
+            ws.warp_scratch_bytes = hybrid_plus_scratch_bytes(chunk, h, w);
+            ws.warp_scratch = take(ws.warp_scratch_bytes);
         }
     }
     ws.total = off;
@@ -135,7 +140,10 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
 static cudaError_t launch_fill(const WarpArgs& a, cudaStream_t s) {
     switch (a.fill) {
         case CS_FILL_NONE: case CS_FILL_NAIVE: case CS_FILL_NAIVE_INTERP: case CS_FILL_INVERSE:
+        case CS_FILL_NONE_POST: case CS_FILL_INVERSE_POST:
             return launch_warp_rows(a, s);
+        case CS_FILL_HYBRID_EDGE_PLUS:
+            return launch_hybrid_plus(a, s);
         case CS_FILL_POLYLINES_SOFT: case CS_FILL_POLYLINES_SHARP:
             return launch_polylines(a, s);
         case CS_FILL_HYBRID_EDGE:
@@ -312,7 +320,8 @@ int cs_shift_indices(const float* nd, int n, int h, int w, double div_px, double
 
 size_t cs_warp_fill_scratch_bytes(int n, int h, int w) {
     (void)w;
-    return align_up((size_t)n * sizeof(FrameStats)) + align_up(polylines_scratch_bytes(n, h));
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(polylines_scratch_bytes(n, h)) +
+           align_up(hybrid_plus_scratch_bytes(n, h, w));
 }
 
 int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int w, int fill, double divergence,
@@ -320,7 +329,7 @@ int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int 
                  size_t scratch_bytes, void* stream) {
     if (!image_u8 || !depth || !out_u8 || !scratch || n < 1 || h < 1 || w < 1)
         return fail(CS_ERR_ARG, "cs_warp_fill: bad argument");
-    if (fill < CS_FILL_NONE || fill > CS_FILL_HYBRID_EDGE) return fail(CS_ERR_ARG, "cs_warp_fill: fill %d is not a CPU technique", fill);
+    if (!is_cpu_technique(fill)) return fail(CS_ERR_ARG, "cs_warp_fill: fill %d is not a CPU technique", fill);
     if (scratch_bytes < cs_warp_fill_scratch_bytes(n, h, w)) return fail(CS_ERR_WORKSPACE, "cs_warp_fill: scratch too small");
     cudaStream_t s = (cudaStream_t)stream;
     FrameStats* st = (FrameStats*)scratch;
@@ -343,6 +352,10 @@ int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int 
     a.expo = exponent;
     a.conv = (float)convergence;
     a.scratch = rest; a.scratch_bytes = polylines_scratch_bytes(n, h);
+    if (fill == CS_FILL_HYBRID_EDGE_PLUS) {
+        a.scratch = rest + align_up(polylines_scratch_bytes(n, h));
+        a.scratch_bytes = hybrid_plus_scratch_bytes(n, h, w);
+    }
     a.flags = g_test_flags;
     cudaError_t e = launch_fill(a, s);
     if (e != cudaSuccess) return cuda_fail(e, "warp/fill");

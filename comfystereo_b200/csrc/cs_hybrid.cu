@@ -166,4 +166,44 @@ cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// hybrid_edge_plus (SIG:1778-1802): pixels the hybrid result leaves black take the polylines_soft pixel.
+__global__ void __launch_bounds__(256) k_merge_black(uint32_t* __restrict__ primary, const uint32_t* __restrict__ fallback,
+                                                     int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t p = primary[i];
+        if ((p & 0x00FFFFFFu) == 0u) primary[i] = fallback[i] & 0x00FFFFFFu;
+    }
+}
+
+static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+size_t hybrid_plus_scratch_bytes(int n, int h, int w) {
+    return 2 * up256((size_t)n * h * w * 4) + up256(polylines_scratch_bytes(n, h));
+}
+
+cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s) {
+    if (a.scratch_bytes < hybrid_plus_scratch_bytes(a.n, a.h, a.w)) return cudaErrorInvalidValue;
+    cudaError_t e = launch_hybrid(a, s);
+    if (e != cudaSuccess) return e;
+    const size_t eye_bytes = up256((size_t)a.n * a.h * a.w * 4);
+    WarpArgs p = a;
+    p.fill = CS_FILL_POLYLINES_SOFT;
+    p.out[0] = reinterpret_cast<uint32_t*>(a.scratch);
+    p.out[1] = reinterpret_cast<uint32_t*>((char*)a.scratch + eye_bytes);
+    p.scratch = (char*)a.scratch + 2 * eye_bytes;
+    p.scratch_bytes = polylines_scratch_bytes(a.n, a.h);
+    if ((e = cudaMemsetAsync((char*)p.scratch + p.scratch_bytes - 16 * sizeof(int), 0, 16 * sizeof(int), s)) != cudaSuccess) return e;
+    if ((e = launch_polylines(p, s)) != cudaSuccess) return e;
+    const int64_t total = (int64_t)a.n * a.h * a.w;
+    int bx = (int)((total + 255) / 256);
+    if (bx > 148 * 16) bx = 148 * 16;
+    for (int eye = 0; eye < 2; ++eye) {
+        if (a.eye[eye].passthrough || !a.out[eye]) continue;
+        prof_begin(K_MISC, s);
+        k_merge_black<<<bx, 256, 0, s>>>(a.out[eye], p.out[eye], total);
+        prof_end(K_MISC, s);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace cs

@@ -169,6 +169,8 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s);       // none /
 cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s);       // soft / sharp
 cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s);          // hybrid_edge (2 kernels)
 size_t polylines_scratch_bytes(int n, int h);
+size_t hybrid_plus_scratch_bytes(int n, int h, int w);
+cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s);     // hybrid_edge_plus (hybrid + polylines_soft + merge)
 cudaError_t launch_minmax(const float* src, int n, int64_t npx, FrameStats* stats, cudaStream_t s);
 cudaError_t launch_export_stats(const FrameStats* stats, int n, int which, float* out, int stride, cudaStream_t s);
 cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, int h, int w, int mode,

@@ -70,7 +70,26 @@ __device__ __forceinline__ int bit_dist_left(const uint32_t* bits, int x, int li
 
 __device__ __forceinline__ int px_sum(uint32_t p) { return (int)(p & 255) + (int)((p >> 8) & 255) + (int)((p >> 16) & 255); }
 
-template <int FILL>  // CS_FILL_NONE / NAIVE / NAIVE_INTERP / INVERSE
+// np.interp row fill of the *_post variants (SIG:1804-1833): left of the first valid column its value, right of the
+// last one its value, between two valid columns  slope = (y1 - y0) / (x1 - x0);  slope * (x - x0) + y0  in float64,
+// stored as float32, truncated to uint8.  `xl`, `xr` are the nearest valid columns (-1 / w when there is none).
+__device__ __forceinline__ uint32_t interp_px(int x, int xl, int xr, int w, uint32_t pl, uint32_t pr) {
+    if (xl < 0) return pr & 0x00FFFFFFu;
+    if (xr >= w) return pl & 0x00FFFFFFu;
+    uint32_t o = 0;
+    const double dx = (double)xr - (double)xl, t = (double)x - (double)xl;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const double y0 = (double)((pl >> (8 * ch)) & 255u), y1 = (double)((pr >> (8 * ch)) & 255u);
+        const double slope = (y1 - y0) / dx;
+        const double v = slope * t;
+        const float rf = (float)(v + y0);
+        o |= ((uint32_t)(int)rf & 255u) << (8 * ch);
+    }
+    return o;
+}
+
+template <int FILL>  // CS_FILL_NONE / NAIVE / NAIVE_INTERP / INVERSE / NONE_POST / INVERSE_POST
 __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
@@ -83,7 +102,7 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
     const uint32_t* img = a.image_u8 + (int64_t)frame * a.h * w + row_off;
     uint32_t* out = a.out[eye] + (int64_t)frame * a.h * w + row_off;
 
-    if (FILL == CS_FILL_INVERSE) {
+    if (FILL == CS_FILL_INVERSE || FILL == CS_FILL_INVERSE_POST) {
         unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
         for (int x = threadIdx.x; x < w; x += blockDim.x) key[x] = 0ull;
         __syncthreads();
@@ -101,6 +120,33 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
             if (j + 1 >= 0 && j + 1 < w) atomicMax(&key[j + 1], k);
         }
         __syncthreads();
+        if (FILL == CS_FILL_INVERSE_POST) {
+            uint32_t* bits = reinterpret_cast<uint32_t*>(key + w);
+            const int wpad = nwords << 5;
+            for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
+                bool f = (x < w) && (key[x] != 0ull);
+                uint32_t b = __ballot_sync(0xffffffffu, f);
+                if ((threadIdx.x & 31) == 0) bits[x >> 5] = b;
+            }
+            __syncthreads();
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                unsigned long long k = key[x];
+                uint32_t px;
+                if (k) px = (img[0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull)] & 0x00FFFFFFu) | 0x01000000u;
+                else {
+                    const int dr = bit_dist_right(bits, nwords, x, 1 << 29), dl = bit_dist_left(bits, x, 1 << 29);
+                    const int xl = (dl < (1 << 29)) ? x - dl : -1, xr = (dr < (1 << 29)) ? x + dr : w;
+                    if (xl < 0 && xr >= w) px = 0u;   // no valid column in the row: it stays as mapped (black)
+                    else {
+                        const uint32_t pl = xl >= 0 ? img[0xFFFFFFFFu - (uint32_t)(key[xl] & 0xFFFFFFFFull)] : 0u;
+                        const uint32_t pr = xr < w ? img[0xFFFFFFFFu - (uint32_t)(key[xr] & 0xFFFFFFFFull)] : 0u;
+                        px = interp_px(x, xl, xr, w, pl, pr);
+                    }
+                }
+                out[x] = px;
+            }
+            return;
+        }
         for (int x = threadIdx.x; x < w; x += blockDim.x) {
             unsigned long long k = key[x];
             uint32_t px = 0;
@@ -137,6 +183,19 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
             for (int x = threadIdx.x; x < w; x += blockDim.x) {
                 int s = win[x];
                 out[x] = (s != empty) ? ((img[s] & 0x00FFFFFFu) | 0x01000000u) : 0u;
+            }
+        } else if (FILL == CS_FILL_NONE_POST) {
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                int s = win[x];
+                uint32_t px;
+                if (s != empty) px = (img[s] & 0x00FFFFFFu) | 0x01000000u;
+                else {
+                    const int dr = bit_dist_right(bits, nwords, x, 1 << 29), dl = bit_dist_left(bits, x, 1 << 29);
+                    const int xl = (dl < (1 << 29)) ? x - dl : -1, xr = (dr < (1 << 29)) ? x + dr : w;
+                    if (xl < 0 && xr >= w) px = 0u;
+                    else px = interp_px(x, xl, xr, w, xl >= 0 ? img[win[xl]] : 0u, xr < w ? img[win[xr]] : 0u);
+                }
+                out[x] = px;
             }
         } else if (FILL == CS_FILL_NAIVE) {
             double adiv = fabs(div_px);
@@ -215,6 +274,16 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_warp_rows<CS_FILL_NAIVE_INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_warp_rows<CS_FILL_NAIVE_INTERP><<<grid, 256, smem, s>>>(a);
+            break;
+        case CS_FILL_NONE_POST:
+            smem = (size_t)a.w * 4 + nwords * 4;
+            k_warp_rows<CS_FILL_NONE_POST><<<grid, 256, smem, s>>>(a);
+            break;
+        case CS_FILL_INVERSE_POST:
+            smem = (size_t)a.w * 8 + nwords * 4;
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_warp_rows<CS_FILL_INVERSE_POST><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_INVERSE:
             smem = (size_t)a.w * 8;

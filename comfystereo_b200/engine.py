@@ -21,6 +21,9 @@ FILL_NAME_TO_KEY = {  # the node's dropdown labels -> dispatch keys, GS:88-100
     'Fill - Naive interpolating': 'naive_interpolating',
     'Fill - Polylines Soft': 'polylines_soft',
     'Fill - Polylines Sharp': 'polylines_sharp',
+    'Fill - Post-fill': 'none_post',                              # GS:97-99: still mapped, no longer in the dropdown
+    'Fill - Reverse projection with Post-fill': 'inverse_post',
+    'Fill - Hybrid Edge with fill': 'hybrid_edge_plus',
 }
 
 

@@ -12,7 +12,7 @@ import torch
 from . import engine
 
 _CPU_FILLS = ('none', 'naive', 'naive_interpolating', 'polylines_soft', 'polylines_sharp', 'inverse',
-              'hybrid_edge')
+              'hybrid_edge', 'none_post', 'inverse_post', 'hybrid_edge_plus')
 _ALL_MODES = engine.MODES
 
 

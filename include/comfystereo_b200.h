@@ -53,7 +53,12 @@ typedef enum cs_fill {
     CS_FILL_POLYLINES_SHARP = 4, /* 'polylines_sharp'      SIG:1912-1992 */
     CS_FILL_INVERSE = 5,         /* 'inverse'              SIG:1715-1737 */
     CS_FILL_HYBRID_EDGE = 6,     /* 'hybrid_edge'          SIG:1837-1848 */
-    CS_FILL_GPU_WARP = 7         /* 'gpu_warp' = forward_warp_gpu, SIG:277-450 */
+    CS_FILL_GPU_WARP = 7,        /* 'gpu_warp' = forward_warp_gpu, SIG:277-450 */
+    /* reachable through create_stereoimages(fill_technique=...) and three dropdown names the node still maps
+     * (GS:97-99) but no longer lists: */
+    CS_FILL_NONE_POST = 8,       /* 'none_post'         SIG:1804-1818: naive mapping + np.interp row fill */
+    CS_FILL_INVERSE_POST = 9,    /* 'inverse_post'      SIG:1820-1833: reverse projection + np.interp row fill */
+    CS_FILL_HYBRID_EDGE_PLUS = 10 /* 'hybrid_edge_plus' SIG:1778-1802: hybrid edge, black pixels from polylines_soft */
 } cs_fill;
 
 /* composition modes, SIG:1543-1562 / SIG:1093-1120 */

@@ -164,6 +164,17 @@ def stage_cases():
     return cases
 
 
+def stage_cases_post():
+    """Second generation of stage fixtures (appended, existing files untouched): the post-fill variants."""
+    cases = []
+    for kind in ("scene", "noise", "quant", "steps", "flat"):
+        for (div, sep, expo, conv) in ((12.0, 0.0, 2.0, 0.5), (-9.0, 1.5, 1.0, 0.0), (7.0, -2.0, 0.7, 1.0)):
+            for fill in ("none_post", "inverse_post", "hybrid_edge_plus"):
+                cases.append(dict(stage="warp", kind=kind, h=24, w=300, seed=500 + len(cases), fill=fill,
+                                  div=div, sep=sep, expo=expo, conv=conv))
+    return cases
+
+
 def run_stage(spec):
     sig = ref_loader.load_sig()
     h, w = spec["h"], spec["w"]
@@ -189,6 +200,22 @@ def run_stage(spec):
                                             spec["expo"], spec["conv"])
         return dict(crc=crc(img, d), warped=warped[0].numpy(), mask=mask[0].numpy().astype(np.uint8))
     raise ValueError(spec["stage"])
+
+
+def main_post():
+    """python oracle/make_golden.py post  -- appends the post-fill stage fixtures to the manifest."""
+    assert ref_loader.reference_available(), "needs /root/reference"
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    manifest["stage"] = [s for s in manifest["stage"] if not s["name"].startswith("post_")]
+    for i, spec in enumerate(stage_cases_post()):
+        rec = run_stage(spec)
+        spec["name"] = f"post_{i:03d}"
+        np.savez_compressed(os.path.join(GOLDEN, f"stage_{spec['name']}.npz"), **rec)
+        manifest["stage"].append(spec)
+    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+    print("post-fill stage cases:", len(stage_cases_post()))
 
 
 def main():
@@ -224,4 +251,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "post":
+        main_post()
+    else:
+        main()

@@ -30,6 +30,9 @@ FILL_NAME_TO_KEY = {  # GS:88-100
     'Fill - Naive interpolating': 'naive_interpolating',
     'Fill - Polylines Soft': 'polylines_soft',
     'Fill - Polylines Sharp': 'polylines_sharp',
+    'Fill - Post-fill': 'none_post',                              # GS:97-99: mapped but commented out of the dropdown
+    'Fill - Reverse projection with Post-fill': 'inverse_post',
+    'Fill - Hybrid Edge with fill': 'hybrid_edge_plus',
 }
 
 
@@ -154,6 +157,33 @@ def hybrid_edge(img, nd, div_px, sep_px, expo):
     return out
 
 
+def interp_rows(base, mask):
+    """np.interp row fill of the *_post variants, SIG:1804-1833."""
+    base, mask = _c(base, np.uint8), _c(mask, np.uint8)
+    H, W = mask.shape
+    out = np.empty_like(base)
+    lib().orc_interp_rows(_p(base), _p(mask), H, W, _p(out))
+    return out
+
+
+def naive_post(img, nd, div_px, sep_px, expo):
+    base, src = naive(img, nd, div_px, sep_px, expo, 'none', want_src=True)
+    return interp_rows(base, (src >= 0).astype(np.uint8))
+
+
+def inverse_post(img, nd, div_px, sep_px, expo):
+    base, mask = inverse(img, nd, div_px, sep_px, expo, want_mask=True)
+    return interp_rows(base, mask)
+
+
+def hybrid_edge_plus(img, nd, div_px, sep_px, expo):
+    prim = hybrid_edge(img, nd, div_px, sep_px, expo)
+    poly = polylines(img, nd, div_px, sep_px, expo, False)
+    out = np.empty_like(prim)
+    lib().orc_merge_black(_p(prim), _p(poly), ctypes.c_int64(prim.shape[0] * prim.shape[1]), _p(out))
+    return out
+
+
 def compose_u8(left, right, mode):
     left, right = _c(left, np.uint8), _c(right, np.uint8)
     H, W, _ = left.shape
@@ -192,6 +222,12 @@ def apply_stereo_divergence(img_u8, depth, divergence, separation, expo, fill, c
         return inverse(img_u8, nd, div_px, sep_px, expo)
     if fill == 'hybrid_edge':
         return hybrid_edge(img_u8, nd, div_px, sep_px, expo)
+    if fill == 'none_post':
+        return naive_post(img_u8, nd, div_px, sep_px, expo)
+    if fill == 'inverse_post':
+        return inverse_post(img_u8, nd, div_px, sep_px, expo)
+    if fill == 'hybrid_edge_plus':
+        return hybrid_edge_plus(img_u8, nd, div_px, sep_px, expo)
     return img_u8  # SIG:1620 fallback
 
 

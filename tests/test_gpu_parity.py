@@ -67,7 +67,7 @@ def test_warp_stage(gu, spec):
     probe = syn.index_probe_image(spec["h"], spec["w"])
     d255 = _stage_depth(spec) * np.float32(255)
     out = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"])[..., :3]
-    if spec["fill"] == "hybrid_edge":
+    if spec["fill"].startswith("hybrid_edge"):
         diff = np.abs(out.astype(np.int32) - g["out"].astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3
     else:
@@ -299,3 +299,34 @@ def test_errors_match_reference(gu, node):
     res = sig.create_stereoimages(img, d, 3.0, fill_technique="no_such_fill")   # SIG:1620: image unchanged
     want = np.clip(img.permute(1, 2, 0).numpy() * np.float32(255), 0, 255).astype(np.uint8)
     assert np.array_equal(np.asarray(res[0][0]), np.hstack([want, want]))
+
+
+@pytest.mark.parametrize("name,key", [("Fill - Post-fill", "none_post"),
+                                      ("Fill - Reverse projection with Post-fill", "inverse_post"),
+                                      ("Fill - Hybrid Edge with fill", "hybrid_edge_plus")])
+def test_post_fill_variants_node_and_function_level(gu, oracle, node, name, key):
+    """The three techniques the node still maps (GS:97-99) but no longer lists, through the node by name and through
+    create_stereoimages by key, against the oracle (itself pinned to the reference by the post_* stage fixtures)."""
+    from comfystereo_b200 import stereoimage_generation as sig
+    img = syn.make_image(2, 40, 120, seed=41)
+    dep = syn.make_depth(2, 40, 120, "scene", seed=41)
+    params = dict(divergence=8.0, separation=0.5, modes="left-right", stereo_balance=0.1, convergence_point=0.5,
+                  stereo_offset_exponent=2.0, fill_technique=name, depth_blur_edge_threshold=20.0,
+                  depth_blur_strength=20.0, depth_map_blur=True, depth_blur_falloff=2.0, depth_blur_vert_smooth=6,
+                  batch_size=12)
+    got = [o.numpy() for o in node.generate(torch.from_numpy(img), torch.from_numpy(dep), **params)]
+    want = oracle.node_generate(img, dep, **params)
+    tol = 1 if key == "hybrid_edge_plus" else 0
+    assert np.abs(gu.q8(got[0]).astype(np.int32) - gu.q8(want[0]).astype(np.int32)).max() <= tol
+    assert np.array_equal(gu.q8(got[1]), gu.q8(want[1])) and np.array_equal(gu.q8(got[2]), gu.q8(want[2]))
+    if tol == 0:
+        assert np.array_equal(got[3], want[3])
+    res = sig.create_stereoimages(torch.from_numpy(img[0]).permute(2, 0, 1), torch.from_numpy(dep[0, ..., 0]), 8.0, 0.5,
+                                  ["left-right", "red-cyan-anaglyph"], 0.1, 2.0, key, 20.0, 20.0, True,
+                                  convergence_point=0.5, depth_blur_falloff=2.0, depth_blur_vert_smooth=6)
+    ref, ml, mr = oracle.create_stereoimages(img[0].transpose(2, 0, 1), dep[0, ..., 0], 8.0, 0.5,
+                                             ["left-right", "red-cyan-anaglyph"], 0.1, 2.0, key, 20.0, 20.0, True, 0.5, 2.0, 6)
+    assert len(res) == 3 and len(res[0]) == 2
+    for a, b in zip(res[0], ref):
+        assert np.abs(np.asarray(a).astype(np.int32) - b.astype(np.int32)).max() <= tol
+    assert np.array_equal(np.asarray(res[1]), ml) and np.array_equal(np.asarray(res[2]), mr)
