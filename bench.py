@@ -44,7 +44,7 @@ BYTES_PER_PX = {"cpu_sbs": 80, "gw_sbs": 76, "anaglyph": 64}  # SURVEY.md 8(d): 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=16, help="frames per GPU per step")
@@ -195,7 +195,8 @@ def main():
     key = engine.FILL_NAME_TO_KEY.get(args.fill, "gpu_warp")
     group = min(NODE_PARAMS["batch_size"], n) if key == "gpu_warp" else 0
     p = engine.make_params(key, args.mode, args.divergence, 0.0, 0.0, 0.5, 2.0, True, 20.0, 20.0, 2.0, 6, group_size=group)
-    img_np, dep_np = make_frames(n, h, w, seed=rank)
+    # every rank gets the same frames: weak scaling means identical work per GPU (polylines cost depends on content)
+    img_np, dep_np = make_frames(n, h, w, seed=0)
     img_h = torch.from_numpy(img_np).pin_memory()
     dep_h = torch.from_numpy(dep_np).pin_memory()
     img_d, dep_d = img_h.to(dev), dep_h.to(dev)
