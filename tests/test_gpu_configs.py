@@ -137,3 +137,35 @@ def test_sharding_invariance_gpuwarp_groups(node):
             parts.append(run(node, img[lo:hi], dep[lo:hi], fill_technique="GPU Warp (Fast)", batch_size=bs, divergence=6.0)[0])
     for k in range(4):
         assert np.array_equal(full[k], np.concatenate([p_[k] for p_ in parts]))
+
+
+ALL_FILLS = ['GPU Warp (Fast)', 'No fill', 'No fill - Reverse projection', 'Imperfect fill - Hybrid Edge', 'Fill - Naive',
+             'Fill - Naive interpolating', 'Fill - Polylines Soft', 'Fill - Polylines Sharp', 'Fill - Post-fill',
+             'Fill - Reverse projection with Post-fill', 'Fill - Hybrid Edge with fill']
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (5, 7), (1, 33), (9, 2), (64, 1025)])
+@pytest.mark.parametrize("fill", ALL_FILLS)
+def test_ragged_sizes_against_oracle(node, oracle, shape, fill):
+    """Widths that are not multiples of 4 (scalar tails of every vectorised kernel), single rows, two-pixel rows,
+    a width just past a power of two -- every technique, every output, against the oracle."""
+    h, w = shape
+    n = 3
+    img = syn.make_image(n, h, w, seed=60 + h + w)
+    dep = syn.make_depth(n, h, w, "scene", seed=60 + h + w)
+    for mode, blur in (("left-right", True), ("top-bottom", False), ("red-cyan-anaglyph", True)):
+        got, p = run(node, img, dep, fill_technique=fill, modes=mode, depth_map_blur=blur, divergence=7.0,
+                     separation=0.7, stereo_balance=-0.2, batch_size=2)
+        want = oracle.node_generate(img, dep, **p)
+        for g, w_ in zip(got, want):
+            assert g.shape == w_.shape
+        if fill == 'GPU Warp (Fast)':
+            assert np.array_equal(got[3], want[3])
+            assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+            assert np.abs(got[0] - want[0]).max() <= 1e-6
+        else:
+            tol = 1 if 'Hybrid' in fill else 0
+            assert np.abs(q8(got[0]).astype(np.int32) - q8(want[0]).astype(np.int32)).max() <= tol
+            assert np.array_equal(q8(got[1]), q8(want[1])) and np.array_equal(q8(got[2]), q8(want[2]))
+            if tol == 0:
+                assert np.array_equal(got[3], want[3])
