@@ -218,8 +218,14 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                for (int l = 0; l < w; ++l) {
-                    if (px_sum(row[l]) != 0 || ((bits[l >> 5] >> (l & 31)) & 1u)) continue;
+                // only unfilled pixels can start a gap: walk the zero bits of the filled map instead of every column
+                for (int wi = 0; wi < nwords; ++wi) {
+                  uint32_t um = ~bits[wi];
+                  if (((wi + 1) << 5) > w) um &= (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+                  while (um) {
+                    const int l = (wi << 5) + __ffs(um) - 1;
+                    um &= um - 1;
+                    if (px_sum(row[l]) != 0) continue;
                     uint32_t lb = (l > 0) ? row[l - 1] : 0u, rb = 0u;
                     int r = l + 1;
                     while (r < w) {
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
                         }
                         row[c] = px;
                     }
+                  }
                 }
             }
             __syncthreads();
