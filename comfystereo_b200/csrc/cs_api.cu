@@ -413,6 +413,15 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     if ((uintptr_t)workspace % 256) return fail(CS_ERR_ARG, "cs_stereo_batch: workspace must be 256-byte aligned");
     const bool cpu = is_cpu_technique(p->fill);
     if (cpu && c != 1 && c != 3) return fail(CS_ERR_ARG, "cs_stereo_batch: depth must have 1 or 3 channels");
+    // one image row lives in shared memory (227 KB per CTA): say so up front instead of failing at launch
+    {
+        const bool sharp = p->fill == CS_FILL_POLYLINES_SHARP;
+        const bool soft = p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_HYBRID_EDGE_PLUS;
+        const int wmax = sharp ? 8000 : (soft ? 12000 : (p->fill == CS_FILL_GPU_WARP ? 9500 : 16000));
+        if (w > wmax)
+            return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
+                        "(one row per CTA in shared memory)", w, wmax);
+    }
     // largest chunk that fits; GPU Warp couples frames inside a sub-batch (Q9), so chunks are whole sub-batches
     const int group = (!cpu && p->group_size > 0) ? (p->group_size < n ? p->group_size : n) : 1;
     const size_t per = cs_workspace_bytes(p, group, h, w);

@@ -94,7 +94,10 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     int ho, wo, hm, wm;
     int rc = cs_output_dims(p, h, w, &ho, &wo, &hm, &wm);
     if (rc) return rc;
+    int prev_device = -1;
+    HOST_CUDA(cudaGetDevice(&prev_device));
     HOST_CUDA(cudaSetDevice(device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};   // leave the caller's device as found
 
     const size_t px = (size_t)h * w;
     const size_t b_img = px * 3 * 4, b_dep = px * c * 4, b_st = (size_t)ho * wo * 3 * 4, b_d = px * 3 * 4, b_m = (size_t)hm * wm * 4;
