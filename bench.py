@@ -288,6 +288,26 @@ def main():
                                     "gbs": k_bytes_px.get(k, 0) * px_step * args.steps / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None}
                                 for k, v in timed.items()}}
 
+    # ---- single-frame latency of BASELINE.json configs[0] and configs[1] (report them as latency)
+    latency = None
+    if rank == 0:
+        latency = {}
+        for name, (lh, lw, lfill, lblur) in {"config0_512x512_naive": (512, 512, "naive", False),
+                                             "config1_1080p_polylines_sharp_blur": (1080, 1920, "polylines_sharp", True)}.items():
+            li, ld = make_frames(1, lh, lw, seed=7)
+            li, ld = torch.from_numpy(li).to(dev), torch.from_numpy(ld).to(dev)
+            lp = engine.make_params(lfill, "left-right", 3.5, 0.0, 0.0, 0.5, 2.0, lblur, 20.0, 20.0, 2.0, 6)
+            lo = engine.stereo_batch_device(li, ld, lp)
+            ts = []
+            for _ in range(30):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                engine.stereo_batch_device(li, ld, lp, out=lo)
+                a1.record()
+                a1.synchronize()
+                ts.append(a0.elapsed_time(a1) * 1e3)
+            latency[name] = {"median_us": float(np.median(ts)), "min_us": float(np.min(ts))}
+
     # ---- end to end through the node with host tensors
     e2e = None
     if not args.no_e2e:
@@ -332,7 +352,7 @@ def main():
             "config": workload_config(args, n),
             "mpix_per_s": fps * h * w / 1e6,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "single_frame_latency": latency,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
