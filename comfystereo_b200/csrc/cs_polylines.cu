@@ -1,25 +1,26 @@
 // cs_polylines.cu -- P: apply_stereo_divergence_polylines (SIG:1912-1992), soft and sharp.
 //
-// One CTA per (row, frame, eye); the whole row lives in shared memory.
+// One CTA per (row, frame, eye); the whole row lives in shared memory.  Two kernels:
 //
-//   points    thread per source column: coord_d in FP64, x = col + 0.5 + coord_d + sep rounded to
-//             float32, closeness |coord_d| float32; sharp emits x -+ 0.45 (two points per column).
-//             Sentinels (-W, 0, col 0) and (2W, 0, col W-1) bracket the row.          SIG:1919-1936
-//   sort      the reference's stable insertion sort by x (segments ride along, SIG:1941-1946) is
-//             replaced by a counting sort: bucket = floor(x) clamped to [-1, W], shared-memory
-//             histogram + CTA scan, then every point ranks itself inside its (tiny) bucket by
-//             (x, source index).  Stable, deterministic, O(points).
-//   cover     output column c owns the sorted points of bucket c; the sub-intervals the reference
-//             visits for c are (pred, b0), (b0, b1), ..., (b_last, succ)               SIG:1955-1961
-//   fast sweep (k_polylines) thread per output column.  The reference's "active list" at a centre
-//             ctr is the SET of segments with x0 < ctr <= x1; the thread finds it by walking back
-//             from the interval's left point while a prefix maximum of segment ends still reaches
-//             ctr.  Selection (max interpolated closeness with 0 < ip < 1) is done in FP64 exactly
-//             as the reference does.  The set is enough unless the choice depends on the ORDER of
-//             the reference's append / swap-remove list -- an exact closeness tie or "no valid
-//             candidate" (Q7).  Such a row raises a flag and is redone by
-//   exact sweep (k_polylines_exact) the same points/sort, then ONE thread replays the reference's
-//             sequential sweep with its list semantics, bit for bit.  Slow, rare on real depth.
+// k_polylines<PER>  the fast path (rows up to ~4090 px sharp / ~8190 px soft)
+//   A points   thread per source column: coord_d in FP64, x = col + 0.5 + coord_d + sep rounded to float32,
+//              closeness |coord_d| float32; sharp emits x -+ 0.45.  Sentinels (-W, 0) and (2W, 0).   SIG:1919-1936
+//   B,C sort   the reference's stable insertion sort by x (SIG:1941-1946) without sorting: shifts are bounded, so the
+//              table is nearly sorted.  Two CTA scans (prefix max / suffix min in source order) tell every point
+//              whether anything before it is larger or anything after it smaller; if not, its rank is its source
+//              index.  The others go to a work list and count their inversions in the window the scans bound.
+//   D,D2 sets  the reference's "active list" at a centre is the SET of segments with x0 < ctr <= x1.  A prefix max
+//              of segment ends (sorted order) bounds the search.  Per sorted interval the set is constant; intervals
+//              with one candidate, or two whose order cannot change inside the interval, are resolved here.
+//   E sweep    thread per output column; the sub-intervals of column c are (pred, b0), (b0, b1), ... of the sorted
+//              points in bucket c (SIG:1955-1961).  Selection and colour accumulation reproduce the reference's
+//              FP64 / float32 rounding sequence.  Choices that depend on the ORDER of the reference's append /
+//              swap-remove list (exact ties, no valid candidate -- quirk Q7) are replayed from the nearest visit
+//              with a single active segment; if that does not fit its budget the row is redone by
+//              sequential_row(), one thread replaying the reference's sweep bit for bit.
+//
+// k_polylines_exact  counting sort + one-thread sequential sweep for every row: serves rows too wide for the fast
+//              kernel's tables and is the independent cross-check of the fast path in the tests.
 //
 // Bytes per pixel and eye: depth 4 B + RGBX8 4 B read (L2-resident scratch), RGBX8 4 B written.
 #include "cs_internal.cuh"
@@ -268,40 +269,18 @@ __global__ void __launch_bounds__(kPolyThreads) k_polylines_exact(const WarpArgs
 // ------------------------------------------------------------------------------------------
 // Conversions between float32 and float64 (F2F / I2F) issue on the 16-lane XU pipe and were the
 // bottleneck of the first version of this kernel (ncu: xu pipe saturated, fp64 pipe 12 % busy).
-// The hot loop therefore never converts: float32 values are widened and float64 sums are rounded
-// to float32 precision with integer bit operations on the ALU pipe, which is exact.
+// The hot loop therefore never converts: the sorted coordinates are widened once per point, uint8
+// colours are widened with a 2^52 bias trick, and float64 sums are rounded to float32 precision on
+// the FP64 pipe.
 
-// exact float32 -> float64 for normal numbers (zero / denormal / inf / nan take the hardware path)
-__device__ __forceinline__ double widen(float f) {
-    uint32_t b = __float_as_uint(f);
-    uint32_t e = (b >> 23) & 0xFFu;
-    if (e == 0u || e == 255u) return (double)f;
-    uint32_t hi = (b & 0x80000000u) | (((b >> 3) & 0x0FFFFFFFu) + 0x38000000u);
-    return __hiloint2double((int)hi, (int)(b << 29));
-}
-// round-to-nearest-even of a float64 to 24 significant bits, result kept as float64.
-// Equals (double)(float)x whenever (float)x is a normal float32.
-__device__ __forceinline__ double round24(double x) {
-    uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
-    uint32_t nlo = lo + 0x0FFFFFFFu + ((lo >> 29) & 1u);
-    hi += (nlo < lo) ? 1u : 0u;
-    return __hiloint2double((int)hi, (int)(nlo & 0xE0000000u));
-}
-// Same rounding on the FP64 pipe (Veltkamp / Dekker split with 2^29 + 1): three FP64 operations instead of seven
-// integer ones.  Identical to round24 except on exact ties (low 29 bits = 100...0), which an accumulated colour
-// sum hits with probability 2^-29 per operation.
+// Round-to-nearest of a float64 to 24 significant bits, result kept as float64: equals
+// (double)(float)x whenever (float)x is a normal float32.  Veltkamp / Dekker split with 2^29 + 1
+// (three FP64 operations).  It differs from IEEE round-half-even only on exact ties (low 29 bits
+// = 100...0), which an accumulated colour sum hits with probability 2^-29 per operation.
 __device__ __forceinline__ double round24_fp(double x) {
     const double g = x * 536870913.0;
     const double d = x - g;
     return g + d;
-}
-// float64 -> float32, round to nearest even, without F2F when the result is a normal float32
-__device__ __forceinline__ float narrow(double x) {
-    uint32_t e = ((uint32_t)__double2hiint(x) >> 20) & 0x7FFu;
-    if (e <= 897u || e >= 1150u) return (float)x;
-    double r = round24(x);
-    uint32_t hi = (uint32_t)__double2hiint(r), lo = (uint32_t)__double2loint(r);
-    return __uint_as_float((hi & 0x80000000u) | (((hi & 0x7FFFFFFFu) - 0x38000000u) << 3) | (lo >> 29));
 }
 // uint8 -> float64 without I2F: 2^52 + v is exact, subtracting 2^52 leaves v
 __device__ __forceinline__ double u8_to_f64(uint32_t v) {
