@@ -197,7 +197,8 @@ CS_API const char *cs_profile_kernel_name(int id);
 CS_API void cs_profile_enable(int on);
 CS_API int cs_profile_collect(double *ms, long long *launches);
 
-/* Test hook.  bit 0: Polylines replays EVERY row with the exact sequential sweep. */
+/* Test hook.  bit 0: Polylines replays EVERY row with the exact sequential sweep.
+ * bit 2: Polylines uses 64-column tiles even when a whole row fits one CTA. */
 CS_API void cs_set_test_flags(int flags);
 
 #ifdef __cplusplus

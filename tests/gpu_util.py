@@ -48,7 +48,7 @@ def blur(d255, strength, thr, falloff, vert):
     return (L[0], R[0], mm.cpu().numpy()) if single else (L, R, mm.cpu().numpy())
 
 
-def warp_fill(img_u8, depth, fill_key, divergence, separation, expo, conv, exact=False):
+def warp_fill(img_u8, depth, fill_key, divergence, separation, expo, conv, exact=False, flags=0):
     """cs_warp_fill on ONE eye: img_u8 [n,h,w,3] or [h,w,3], depth same leading dims.  Returns uint8 [...,4]
     (RGB + the filled/mask flag byte)."""
     img = np.ascontiguousarray(img_u8, np.uint8)
@@ -63,7 +63,7 @@ def warp_fill(img_u8, depth, fill_key, divergence, separation, expo, conv, exact
     lib = _lib.lib()
     nb = lib.cs_warp_fill_scratch_bytes(n, h, w)
     scratch = torch.empty(nb, dtype=torch.uint8, device=dev())
-    lib.cs_set_test_flags(1 if exact else 0)
+    lib.cs_set_test_flags((1 if exact else 0) | flags)
     try:
         _lib.check(lib.cs_warp_fill(ti.data_ptr(), td.data_ptr(), n, h, w, FILL_KEYS.index(fill_key),
                                     float(divergence), float(separation), float(expo), float(conv),

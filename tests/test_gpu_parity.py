@@ -75,6 +75,9 @@ def test_warp_stage(gu, spec):
     if spec["fill"].startswith("polylines"):  # the exact sequential replay must agree with the fast sweep
         ex = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"], exact=True)
         assert np.array_equal(ex[..., :3], g["out"])
+        # and so must the tiled variant used for rows too wide for one CTA (forced here: 64-column tiles)
+        tl = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"], flags=4)
+        assert np.array_equal(tl[..., :3], g["out"])
 
 
 @pytest.mark.parametrize("spec", STAGE["gpuwarp"], ids=[s["name"] + "_" + s["kind"] for s in STAGE["gpuwarp"]])

@@ -1,13 +1,15 @@
-"""Dev telemetry: how many rows of a 1080p benchmark frame fall back to the sequential replay."""
-import ctypes, sys, os, time
+"""Dev telemetry: how many rows of a benchmark frame fall back to the sequential replay."""
+import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from comfystereo_b200 import engine, _lib, synthetic as syn
-h, w = 1080, 1920
+h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1080, 1920)
+div = float(sys.argv[3]) if len(sys.argv) > 3 else 3.5
+bal = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 img = torch.from_numpy(syn.make_image(1, h, w, seed=0)).cuda()
 dep = torch.from_numpy(syn.make_depth(1, h, w, "scene", seed=0)).cuda()
-p = engine.make_params("polylines_sharp", "left-right", 3.5, 0, 0, 0.5, 2.0, True, 20, 20, 2.0, 6)
-for _ in range(3):
+p = engine.make_params("polylines_sharp", "left-right", div, 0, bal, 0.5, 2.0, True, 20, 20, 2.0, 6)
+for _ in range(2):
     engine.stereo_batch_device(img, dep, p, chunk=1)
 torch.cuda.synchronize()
 ws = engine._workspaces[0]
