@@ -169,3 +169,22 @@ def test_ragged_sizes_against_oracle(node, oracle, shape, fill):
             assert np.array_equal(q8(got[1]), q8(want[1])) and np.array_equal(q8(got[2]), q8(want[2]))
             if tol == 0:
                 assert np.array_equal(got[3], want[3])
+
+
+def test_one_process_multi_gpu_sharding(node, oracle):
+    """Inside ComfyUI there is one process: the node shards the batch frame-wise over every visible GPU (one host
+    thread and one pipeline per device, no collective) and assembles in order.  Needs >= 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from comfystereo_b200 import engine
+    n = 9
+    img = syn.make_image(n, 270, 480, seed=71)
+    dep = syn.make_depth(n, 270, 480, "scene", seed=71)
+    for fill, bs in (("Fill - Polylines Sharp", 12), ("GPU Warp (Fast)", 2)):
+        got, p = run(node, img, dep, fill_technique=fill, batch_size=bs, divergence=6.0)   # multi-GPU path (n >= 2 * ndev)
+        key = engine.FILL_NAME_TO_KEY[fill]
+        prm = engine.make_params(key, "left-right", 6.0, 0.0, 0.0, 0.5, 2.0, True, 20.0, 20.0, 2.0, 6,
+                                 group_size=min(bs, n) if key == "gpu_warp" else 0)
+        one = [o.numpy() for o in engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), prm, device=0)]
+        for a, b in zip(got, one):
+            assert np.array_equal(a, b)
