@@ -290,7 +290,7 @@ __device__ __forceinline__ double u8_to_f64(uint32_t v) {
 struct PolyCtx {
     const float* px;        // [npts] source-order x (float32)
     const double* sxd;      // [npts] sorted x, widened
-    const uint32_t* info;   // [npts] sorted -> source point index (low 16 bits) | kSimple
+    const uint32_t* info;   // [npts] sorted -> source point index (low 16 bits) | candidate code (see below)
     const float* reach;     // [npts] prefix max (sorted order) of segment ends
     const float* clo;       // [w + 2] padded: clo[pt_slot(i)] is the closeness of source point i
     const int* start;       // [tw+3] first sorted rank of bucket b = floor(x) - t0 + 1

@@ -44,13 +44,16 @@ def test_no_gpu_means_loud_failure_not_fallback():
 
 
 def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under comfystereo_b200/ may import, link or execute it
+    (comments may mention it)."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "comfystereo_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("the oracle's", "").replace("oracle/stereo_oracle.c", "") \
-                    or f in ("cs_blur.cu",), f"{f} mentions the oracle"
-                assert "import oracle" not in src and "stereo_oracle" not in src.replace("oracle/stereo_oracle.c", "")
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            for line in open(os.path.join(dirpath, f)):
+                code = line.split("//")[0].split("#")[0] if f.endswith((".cu", ".cuh", ".h")) else line.split("#")[0]
+                assert "import oracle" not in code and "stereo_oracle" not in code and "libstereo_oracle" not in code, \
+                    f"{f}: {line.strip()}"
 
 
 def test_params_follow_python_rounding():
