@@ -142,6 +142,21 @@ def stereo_batch_device(image, depth, p, out=None, chunk=None):
     return stereo, dl, dr, mask
 
 
+# Outputs are page-locked (so the D2H copies overlap the kernels) only up to this size: a 300-frame 1080p batch is
+# 35 GB of results, which should not be pinned wholesale on a workstation.
+PIN_LIMIT_BYTES = 4 << 30
+
+
+def _out_bytes(s_shape, d_shape, m_shape):
+    total = 0
+    for shp, k in ((s_shape, 1), (d_shape, 2), (m_shape, 1)):
+        n = 4
+        for v in shp:
+            n *= v
+        total += k * n
+    return total
+
+
 def stereo_batch_host(image, depth, p, device=0, pin_outputs=True):
     """The hot path on CPU tensors (what ComfyUI hands the node): chunks are streamed through the
     GPU with upload, kernels and download overlapped inside the library.  Returns CPU tensors."""
@@ -158,7 +173,7 @@ def stereo_batch_host(image, depth, p, device=0, pin_outputs=True):
         raise AssertionError('Depthmap and the image must have the same size')
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
-    pin = bool(pin_outputs) and torch.cuda.is_available()
+    pin = bool(pin_outputs) and torch.cuda.is_available() and _out_bytes(s_shape, d_shape, m_shape) <= PIN_LIMIT_BYTES
     stereo = torch.empty(s_shape, dtype=torch.float32, pin_memory=pin)
     dl = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
     dr = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
@@ -197,7 +212,7 @@ def stereo_batch_multi_gpu(image, depth, p, devices):
     depth = depth.contiguous().float()
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
-    pin = torch.cuda.is_available()
+    pin = torch.cuda.is_available() and _out_bytes(s_shape, d_shape, m_shape) <= PIN_LIMIT_BYTES
     outs = (torch.empty(s_shape, dtype=torch.float32, pin_memory=pin),
             torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
             torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
