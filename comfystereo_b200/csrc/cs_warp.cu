@@ -99,15 +99,32 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
     float scale;
     const Normalizer norm = eye_normalizer(a, eye, frame, &scale);
     const int64_t row_off = (int64_t)y * w;
-    const uint32_t* img = a.image_u8 + (int64_t)frame * a.h * w + row_off;
     uint32_t* out = a.out[eye] + (int64_t)frame * a.h * w + row_off;
+    // the RGBX8 row is gathered at shifted columns: stage it in shared memory with one coalesced pass (the scattered
+    // global reads were 31 % of this kernel's stall samples), and fetch depth four columns ahead of the FP64 chain
+    uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
+    const size_t simg_bytes = ((size_t)w * 4 + 15) & ~(size_t)15;
+    unsigned char* smem_rest = smem_raw + simg_bytes;
+    {
+        const uint32_t* gimg = a.image_u8 + (int64_t)frame * a.h * w + row_off;
+        for (int x = threadIdx.x; x < w; x += blockDim.x) simg[x] = gimg[x];
+    }
+    const uint32_t* img = simg;
+    const float* dep = a.depth[eye] + (int64_t)frame * a.h * w + row_off;
 
     if (FILL == CS_FILL_INVERSE || FILL == CS_FILL_INVERSE_POST) {
-        unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_rest);
         for (int x = threadIdx.x; x < w; x += blockDim.x) key[x] = 0ull;
         __syncthreads();
-        for (int x = threadIdx.x; x < w; x += blockDim.x) {
-            float nd = norm(eye_depth(a, eye, frame, row_off + x, scale)) + 0.0f;
+        for (int xb = threadIdx.x; xb < w; xb += 4 * blockDim.x) {
+          float dv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const int x = xb + u * blockDim.x; dv[u] = (x < w) ? dep[x] : 0.0f; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int x = xb + u * blockDim.x;
+            if (x >= w) break;
+            float nd = norm(scale == 1.0f ? dv[u] : dv[u] * scale) + 0.0f;
             if (!(nd > -1.0f)) continue;  // z-buffer starts at -1 and the test is strict (SIG:1722, 1731)
             double off = signed_pow_offset(nd, a.expo, div_px);
             double dx = ((double)x + 0.5) + off;
@@ -118,6 +135,7 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)x);
             if (j >= 0 && j < w) atomicMax(&key[j], k);
             if (j + 1 >= 0 && j + 1 < w) atomicMax(&key[j + 1], k);
+          }
         }
         __syncthreads();
         if (FILL == CS_FILL_INVERSE_POST) {
@@ -155,21 +173,29 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
         }
         return;
     } else {
-        int* win = reinterpret_cast<int*>(smem_raw);
+        int* win = reinterpret_cast<int*>(smem_rest);
         uint32_t* bits = reinterpret_cast<uint32_t*>(win + w);
         uint32_t* row = bits + nwords;  // only FILL == NAIVE_INTERP
         const bool take_min = !(div_px < 0);
         const int empty = take_min ? 0x7FFFFFFF : -1;
         for (int x = threadIdx.x; x < w; x += blockDim.x) win[x] = empty;
         __syncthreads();
-        for (int x = threadIdx.x; x < w; x += blockDim.x) {
-            float nd = norm(eye_depth(a, eye, frame, row_off + x, scale));
+        for (int xb = threadIdx.x; xb < w; xb += 4 * blockDim.x) {
+          float dv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const int x = xb + u * blockDim.x; dv[u] = (x < w) ? dep[x] : 0.0f; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int x = xb + u * blockDim.x;
+            if (x >= w) break;
+            float nd = norm(scale == 1.0f ? dv[u] : dv[u] * scale);
             double off = signed_pow_offset(nd, a.expo, div_px);
             double t = off + sep_px;
             int cd = x + (int)t;  // truncation toward zero, SIG:1865
             if (cd >= 0 && cd < w) {
                 if (take_min) atomicMin(&win[cd], x); else atomicMax(&win[cd], x);
             }
+          }
         }
         __syncthreads();
         const int wpad = nwords << 5;
@@ -266,34 +292,35 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
     dim3 grid(a.h, a.n, 2);
     size_t smem;
+    const size_t simg = ((size_t)a.w * 4 + 15) & ~(size_t)15;   // staged RGBX8 row
     prof_begin(K_WARP_ROWS, s);
     switch (a.fill) {
         case CS_FILL_NONE:
-            smem = (size_t)a.w * 4 + nwords * 4;
+            smem = simg + (size_t)a.w * 4 + nwords * 4;
             k_warp_rows<CS_FILL_NONE><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_NAIVE:
-            smem = (size_t)a.w * 4 + nwords * 4;
+            smem = simg + (size_t)a.w * 4 + nwords * 4;
             k_warp_rows<CS_FILL_NAIVE><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_NAIVE_INTERP:
-            smem = (size_t)a.w * 8 + nwords * 4;
+            smem = simg + (size_t)a.w * 8 + nwords * 4;
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_warp_rows<CS_FILL_NAIVE_INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_warp_rows<CS_FILL_NAIVE_INTERP><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_NONE_POST:
-            smem = (size_t)a.w * 4 + nwords * 4;
+            smem = simg + (size_t)a.w * 4 + nwords * 4;
             k_warp_rows<CS_FILL_NONE_POST><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_INVERSE_POST:
-            smem = (size_t)a.w * 8 + nwords * 4;
+            smem = simg + (size_t)a.w * 8 + nwords * 4;
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_warp_rows<CS_FILL_INVERSE_POST><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_INVERSE:
-            smem = (size_t)a.w * 8;
+            smem = simg + (size_t)a.w * 8;
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_warp_rows<CS_FILL_INVERSE><<<grid, 256, smem, s>>>(a);
