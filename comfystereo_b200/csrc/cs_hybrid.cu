@@ -32,6 +32,18 @@ __device__ __forceinline__ Normalizer hy_normalizer(const WarpArgs& a, int eye, 
     return make_normalizer(lo, hi, scale, a.conv);
 }
 
+// float64 -> nearest float32 value, kept as float64 (Veltkamp split, 2^29 + 1), and uint8 -> float64 through the
+// 2^52 bias: the float32 accumulators of the reference are carried in FP64 registers without F2F / I2F conversions,
+// which issue on the 16-lane XU pipe (52 % busy in this kernel before the change).  See cs_polylines.cu.
+__device__ __forceinline__ double hy_round24(double x) {
+    const double g = x * 536870913.0;
+    const double d = x - g;
+    return g + d;
+}
+__device__ __forceinline__ double hy_u8(uint32_t v) {
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
 __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
         // sources with jc in {j-1, j, j+1}:  x = jc - (jc - x)  lies in [j-1-omax, j+1-omin]
         long long lo = (long long)j - 1 - omax, hi = (long long)j + 1 - omin;
         int x0 = (int)max(lo, 0ll), x1 = (int)min(hi, (long long)w - 1);
-        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, ws = 0.0f;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, ws = 0.0;   // float32-valued
         bool hit = false;
         for (int x = x0; x <= x1; ++x) {
             int dj = j - jcs[x];
@@ -82,17 +94,18 @@ __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
             double diff = dxs[x] - (double)j;
             double wg = exp(-(diff * diff) / 2.0);
             uint32_t p = img[x];
-            acc0 = (float)((double)acc0 + (double)(p & 255u) * wg);
-            acc1 = (float)((double)acc1 + (double)((p >> 8) & 255u) * wg);
-            acc2 = (float)((double)acc2 + (double)((p >> 16) & 255u) * wg);
-            ws = (float)((double)ws + wg);
+            acc0 = hy_round24(acc0 + hy_u8(p & 255u) * wg);
+            acc1 = hy_round24(acc1 + hy_u8((p >> 8) & 255u) * wg);
+            acc2 = hy_round24(acc2 + hy_u8((p >> 16) & 255u) * wg);
+            ws = hy_round24(ws + wg);
             hit = true;
         }
         uint32_t px = 0;
-        if (ws > 0.0f) {
-            float v0 = fminf(fmaxf(acc0 / ws, 0.0f), 255.0f);
-            float v1 = fminf(fmaxf(acc1 / ws, 0.0f), 255.0f);
-            float v2 = fminf(fmaxf(acc2 / ws, 0.0f), 255.0f);
+        if (ws > 0.0) {
+            const float wsf = (float)ws;
+            float v0 = fminf(fmaxf((float)acc0 / wsf, 0.0f), 255.0f);
+            float v1 = fminf(fmaxf((float)acc1 / wsf, 0.0f), 255.0f);
+            float v2 = fminf(fmaxf((float)acc2 / wsf, 0.0f), 255.0f);
             px = pack_rgbx((int)v0, (int)v1, (int)v2);
         }
         out[j] = px | (hit ? 0x01000000u : 0u);
