@@ -290,17 +290,18 @@ __device__ __forceinline__ double u8_to_f64(uint32_t v) {
 struct PolyCtx {
     const float* px;        // [npts] source-order x (float32)
     const double* sxd;      // [npts] sorted x, widened
-    const uint32_t* info;   // [npts] sorted -> source point index (low 16 bits) | candidate code (see below)
+    const unsigned short* sidx;   // [npts] sorted rank -> source point index
     const float* reach;     // [npts] prefix max (sorted order) of segment ends
     const float* clo;       // [w + 2] padded: clo[pt_slot(i)] is the closeness of source point i
     const int* start;       // [tw+3] first sorted rank of bucket b = floor(x) - t0 + 1
     int t0;                 // first output column of the tile (0 when the CTA owns the whole row)
     RowCtx row;             // describes the tile's SOURCE window: w = window width, points / segments of the window
 };
-// info[k] (k = sorted rank): bits 0-15 source point index; bits 16-17 number of segments active anywhere strictly
-// inside the interval (sorted point k, sorted point k+1), 3 = "three or more / does not fit"; bits 18-24 and 25-31:
-// how many ranks back the first / second active segment starts.
-constexpr int kCodeShift = 16, kOff1Shift = 18, kOff2Shift = 25;
+// cand[k] (k = sorted rank, uint16): bits 0-1 number of segments active anywhere strictly inside the interval
+// (sorted point k, sorted point k+1), 3 = "three or more / does not fit"; bits 2-8 and 9-15: how many ranks back the
+// first / second active segment starts.  Kept apart from sidx[] so that the threads resolving intervals (writers of
+// cand) never touch words other threads are reading (sidx) -- racecheck-clean.
+constexpr int kOff1Shift = 2, kOff2Shift = 9;
 
 // `col` is the output column relative to the tile
 __device__ __forceinline__ double visit_ctr(const PolyCtx& c, int col, int k, double* sig_out) {
@@ -316,7 +317,7 @@ __device__ __forceinline__ double visit_ctr(const PolyCtx& c, int col, int k, do
 __device__ __forceinline__ int active_count(const PolyCtx& c, int k, double ctr, int* which) {
     int n = 0;
     for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
-        int sp = (int)(c.info[j] & 0xFFFFu);
+        int sp = (int)c.sidx[j];
         if (!(c.sxd[j] < ctr) || ((double)c.px[sp + 1] < ctr)) continue;
         ++n;
         *which = j;
@@ -356,7 +357,7 @@ __device__ __noinline__ int replay_choice(const PolyCtx& c, int col, int k) {
         double ctr = visit_ctr(c, rc, rk, &sig);
         while (sgp < nsg && c.sxd[sgp] < ctr) {
             if (n >= kCap) return -1;
-            lst[n++] = (unsigned short)(c.info[sgp] & 0xFFFFu);
+            lst[n++] = c.sidx[sgp];
             ++sgp;
         }
         for (int i = 0; i < n;) {
@@ -393,7 +394,7 @@ __device__ __noinline__ int general_visit(const PolyCtx& c, int col, int k, doub
     int nact = 0, best = -1, only = -1, nbest = 0;
     double bestc = -kEps;
     for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
-        int sp = (int)(c.info[j] & 0xFFFFu);
+        int sp = (int)c.sidx[j];
         float x0 = c.px[sp], x1 = c.px[sp + 1];
         if (!((double)x0 < ctr) || ((double)x1 < ctr)) continue;
         ++nact;
@@ -429,7 +430,7 @@ __device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* im
             double sig;
             double ctr = visit_ctr(c, col, pi, &sig);
             while (sgp < nsg && c.sxd[sgp] < ctr) {
-                if (nact < act_cap) act[nact++] = (unsigned short)(c.info[sgp] & 0xFFFFu);
+                if (nact < act_cap) act[nact++] = c.sidx[sgp];
                 else overflow = true;
                 ++sgp;
             }
@@ -505,8 +506,9 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     double* sxd = reinterpret_cast<double*>(px + NP);               // [NP]   (aliases pm / sm during the sort)
     float* pm = reinterpret_cast<float*>(sxd);                      // [NP] inclusive prefix max of px
     float* sm = pm + NP;                                            // [NP] inclusive suffix min of px
-    uint32_t* info = reinterpret_cast<uint32_t*>(sxd + NP);         // [NP]
-    float* reach = reinterpret_cast<float*>(info + NP);             // [NP]
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(sxd + NP);   // [NP] sorted rank -> source point
+    unsigned short* cand = sidx + NP;                                     // [NP] per-interval candidate code
+    float* reach = reinterpret_cast<float*>(cand + NP);             // [NP]
     float* clo = reach + NP;                                        // [w + 2] padded closeness table
     int* start = reinterpret_cast<int*>(clo + (w + 4));             // [w + 4]
     uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));  // [w]
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             if (i < npts) {
                 const int r = (dirty_bits & (1u << e)) ? (int)drank[i] : i;
                 sxd[r] = (double)v[e];
-                info[r] = (uint32_t)i;
+                sidx[r] = (unsigned short)i;
             }
         }
     }
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             int kp = i0 - 1;
             if (kp < 0) bprev = -1;
             else if (kp >= npts) bprev = tw + 1;
-            else { float fx = floorf(px[info[kp] & 0xFFFFu]); bprev = (fx < (float)t0) ? 0 : ((fx >= (float)(t0 + tw)) ? tw + 1 : (int)fx - t0 + 1); }
+            else { float fx = floorf(px[sidx[kp]]); bprev = (fx < (float)t0) ? 0 : ((fx >= (float)(t0 + tw)) ? tw + 1 : (int)fx - t0 + 1); }
         }
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             float x1 = -INFINITY;
             avv[e] = 0.0f; spv[e] = 0;
             if (k < npts) {
-                const int sp = (int)(info[k] & 0xFFFFu);
+                const int sp = (int)sidx[k];
                 if (k < nsg) x1 = px[sp + 1];
                 const float pv = px[sp];
                 avv[e] = pv; spv[e] = sp;
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 hard |= 1u << e;
             } else {
                 const uint32_t code = (x1v[e] > avv[e]) ? 1u : 0u;
-                info[k] = (uint32_t)spv[e] | (code << kCodeShift);
+                cand[k] = (unsigned short)code;
             }
         }
         if (hard) {
@@ -722,16 +724,16 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
 
     // ---- D2 (second half): active set of the listed intervals (a, b) = (point k, point k+1).  For a centre strictly
     // inside, a segment j is active iff it starts at or before a (j <= k) and ends beyond a; nothing between a and b
-    // is a point, so all of this is float32 comparisons.  Up to two active segments are encoded in info[k].
+    // is a point, so all of this is float32 comparisons.  Up to two active segments are encoded in cand[k].
     {
         const int nlist = s_ntwo;
         for (int q = tid; q < nlist; q += kPolyThreads) {
             const int k = tlist[q];
-            const uint32_t me = info[k] & 0xFFFFu;
+            const uint32_t me = sidx[k];
             const float av = px[me];
             int cnt = 0, o1 = 0, o2 = 0;
             for (int j = k; j >= 0 && reach[j] > av; --j) {
-                const int sp = (int)(info[j] & 0xFFFFu);
+                const int sp = (int)sidx[j];
                 if (px[sp + 1] > av) {
                     if (cnt == 0) o1 = k - j; else if (cnt == 1) o2 = k - j;
                     ++cnt;
@@ -745,8 +747,8 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 // one-candidate interval.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
                 // segment, and ip < 1 can only fail (float32 rounding of x1 - x0) for long segments that end at or just
                 // beyond this interval's right point -- those stay two-candidate and are decided per visit in FP64.
-                const float bv = px[info[k + 1] & 0xFFFFu];
-                const int spA = (int)(info[k - o1] & 0xFFFFu), spB = (int)(info[k - o2] & 0xFFFFu);
+                const float bv = px[sidx[k + 1]];
+                const int spA = (int)sidx[k - o1], spB = (int)sidx[k - o2];
                 const float ax0 = px[spA], ax1 = px[spA + 1], bx0 = px[spB], bx1 = px[spB + 1];
                 const float aq0 = clo[pt_slot(spA, c.sharp)], aq1 = clo[pt_slot(spA + 1, c.sharp)];
                 const float bq0 = clo[pt_slot(spB, c.sharp)], bq1 = clo[pt_slot(spB + 1, c.sharp)];
@@ -764,14 +766,14 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 if (safe && a_lo > b_lo + margin && a_hi > b_hi + margin) code = 1u;                     // first candidate
                 else if (safe && b_lo > a_lo + margin && b_hi > a_hi + margin) { code = 1u; o1 = o2; }  // second candidate
             }
-            info[k] = me | (code << kCodeShift) | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift);
+            cand[k] = (unsigned short)(code | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift));
         }
     }
     __syncthreads();
 
     // ---- E: sweep, one thread per output column
     PolyCtx ctx;
-    ctx.px = px; ctx.sxd = sxd; ctx.info = info; ctx.reach = reach; ctx.clo = clo; ctx.start = start; ctx.row = c;
+    ctx.px = px; ctx.sxd = sxd; ctx.sidx = sidx; ctx.reach = reach; ctx.clo = clo; ctx.start = start; ctx.row = c;
     ctx.t0 = t0;
     uint32_t* out = a.out[eye] + row_off + t0;
     bool give_up = false;
@@ -795,13 +797,13 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             const double to = ((pb < col1d) ? pb : col1d) - kEps;
             const double sig = to - from;
             const double ctr = from + 0.5 * sig;
-            const uint32_t inf = info[k];
-            const uint32_t code = (inf >> kCodeShift) & 3u;
+            const uint32_t inf = cand[k];
+            const uint32_t code = inf & 3u;
             int sp;
             bool resolved = false, off_is_k = false;
             if (code == 1u && sig > 0.0) {
                 const int off1 = (int)((inf >> kOff1Shift) & 127u);
-                sp = (off1 == 0) ? (int)(inf & 0xFFFFu) : (int)(info[k - off1] & 0xFFFFu);
+                sp = (int)sidx[k - off1];
                 off_is_k = (off1 == 0);   // the segment starts at this interval's left point: x0 = pa
                 resolved = true;
             }
