@@ -282,6 +282,15 @@ __device__ __forceinline__ double round24_fp(double x) {
     const double d = x - g;
     return g + d;
 }
+// The same rounding with exact IEEE ties-to-even, in integer arithmetic.  Used where ties are NOT improbable: the
+// float32 subtraction x1 - x0 of two float32 coordinates is a short exact binary number, and when it needs 25 bits
+// (small coordinates, first columns of a row) it is an exact tie half of the time.
+__device__ __forceinline__ double round24_even(double x) {
+    uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+    uint32_t nlo = lo + 0x0FFFFFFFu + ((lo >> 29) & 1u);
+    hi += (nlo < lo) ? 1u : 0u;
+    return __hiloint2double((int)hi, (int)(nlo & 0xE0000000u));
+}
 // uint8 -> float64 without I2F: 2^52 + v is exact, subtracting 2^52 leaves v
 __device__ __forceinline__ double u8_to_f64(uint32_t v) {
     return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
@@ -821,7 +830,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 // ip = (ctr - x0) / (x1 - x0) with the reference's float32 subtraction in the denominator
                 const double x0 = off_is_k ? pa : (double)px[sp];
                 const double x1 = (double)px[sp + 1];
-                const double den = round24_fp(x1 - x0);
+                const double den = round24_even(x1 - x0);
                 const double ip = (ctr - x0) / den;
                 const uint32_t pr = simg[cr];
                 const double om = 1.0 - ip;

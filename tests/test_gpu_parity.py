@@ -333,3 +333,18 @@ def test_post_fill_variants_node_and_function_level(gu, oracle, node, name, key)
     for a, b in zip(res[0], ref):
         assert np.abs(np.asarray(a).astype(np.int32) - b.astype(np.int32)).max() <= tol
     assert np.array_equal(np.asarray(res[1]), ml) and np.array_equal(np.asarray(res[2]), mr)
+
+
+@pytest.mark.parametrize("fill", ["polylines_sharp", "polylines_soft"])
+def test_polylines_small_coordinates_exact(gu, oracle, fill):
+    """Connecting segments whose ends lie below x = 2 make the reference's float32 subtraction x1 - x0 inexact, with
+    exact ties half of the time; 16k random narrow rows exercise exactly that corner of the rounding emulation."""
+    rng = np.random.default_rng(17)
+    h, w = 16384, 8
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    d = rng.random((h, w), dtype=np.float32)
+    for div, sep, expo, conv in ((30.0, -20.0, 1.0, 0.5), (-25.0, 10.0, 2.0, 0.3), (12.0, -6.0, 0.7, 0.9)):
+        got = gu.warp_fill(img, d, fill, div, sep, expo, conv)[..., :3]
+        nd = oracle.normalize(d, conv)
+        want = oracle.polylines(img, nd, (div / 100.0) * w, (sep / 100.0) * w, expo, fill == "polylines_sharp")
+        assert np.array_equal(got, want), f"{(got != want).any(axis=-1).sum()} pixels differ"
