@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
     int* win = reinterpret_cast<int*>(zb + w);
     uint32_t* fbits = reinterpret_cast<uint32_t*>(win + w + 16);   // filled (src >= 0) bitmap
     uint32_t* ubits = fbits + nwords;                         // unfilled in either eye (mask)
+    unsigned char* vm = reinterpret_cast<unsigned char*>(ubits + nwords);   // [w] per pair: rounds in which it can be valid
     __shared__ int s_last;
 
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) ubits[i] = 0u;
@@ -150,9 +151,25 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
         for (int x = threadIdx.x; x < w + 16; x += blockDim.x) M[x] = -1;
         __syncthreads();
         for (int i = threadIdx.x; i + 1 < w; i += blockDim.x) {
-            const float fl = floorf(fminf(dest[i], dest[i + 1]));
+            const float dl = dest[i], dr = dest[i + 1];
+            const float fl = floorf(fminf(dl, dr));
             const int cbc = (fl < -8.0f) ? -8 : ((fl > (float)(w + 7)) ? w + 7 : (int)fl);
             atomicMax(&M[cbc + 8], i);
+            // rounds in which this pair CAN be valid: 0 <= frac < 1 needs (c - dl) between 0 and safe (correctly rounded
+            // division is monotone, so this pre-test only removes pairs the full test below would reject as well)
+            uint32_t vmask = 0;
+            if (fabsf(po[i + 1] - po[i]) < 1.5f && fl >= -8.0f && fl <= (float)(w + 7)) {
+                const float sw = dr - dl;
+                const float safe = (fabsf(sw) < 1e-4f) ? 1.0f : sw;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int c = (int)fl + k;
+                    const float num = (float)c - dl;
+                    const bool pass = (safe > 0.0f) ? (num >= 0.0f && num < safe) : (num <= 0.0f && num > safe);
+                    if (c >= 0 && c < w && pass) vmask |= 1u << k;
+                }
+            }
+            vm[i] = (unsigned char)vmask;
         }
         __syncthreads();
         for (int x = threadIdx.x; x < w; x += blockDim.x) {
@@ -171,6 +188,7 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
                     i = M[x - k + 8];
                 }
                 if (i < 0) continue;
+                if (!((vm[i] >> k) & 1u)) continue;
                 const float dl = dest[i], dr = dest[i + 1];
                 const bool connected = fabsf(po[i + 1] - po[i]) < 1.5f;
                 const float dm = fminf(dl, dr);
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
 
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
-    size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8;
+    size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8 + (size_t)a.w + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_gpuwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
