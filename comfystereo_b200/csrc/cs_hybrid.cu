@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
     if (a.eye[eye].passthrough) return;
     double* dxs = reinterpret_cast<double*>(smem_raw);          // [w] destination x of each source column
     int* jcs = reinterpret_cast<int*>(dxs + w);                 // [w] floor(dest_x)
+    const int nblk = (w + 31) >> 5;
+    int* bmin = jcs + w;                                        // [nblk] min / max of (jc - x) per 32 source columns
+    int* bmax = bmin + nblk;
     __shared__ int s_omin, s_omax;
     if (threadIdx.x == 0) { s_omin = 0x7FFFFFFF; s_omax = (int)0x80000000; }
     const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
@@ -61,19 +64,30 @@ __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
     uint32_t* out = a.out[eye] + row_off;
     __syncthreads();
     int omin = 0x7FFFFFFF, omax = (int)0x80000000;
-    for (int x = threadIdx.x; x < w; x += blockDim.x) {
-        float d = dep[x];
-        if (scale != 1.0f) d = d * scale;
-        double off = signed_pow_offset(norm(d), a.expo, div_px);
-        double dx = ((double)x + 0.5) + off;
-        dx = dx + sep_px;
-        double fl = floor(dx);
-        // keep the index sane for absurd parameters; such columns can never be on screen
-        int jc = (fl < -1.0e9) ? -1000000000 : ((fl > 1.0e9) ? 1000000000 : (int)fl);
-        dxs[x] = dx;
-        jcs[x] = jc;
-        int o = jc - x;
-        omin = min(omin, o); omax = max(omax, o);
+    const int wpad = nblk << 5;
+    for (int x = threadIdx.x; x < wpad; x += blockDim.x) {   // padded to whole warps: the block ranges use full-mask shuffles
+        int lo = 0x7FFFFFFF, hi = (int)0x80000000;
+        if (x < w) {
+            float d = dep[x];
+            if (scale != 1.0f) d = d * scale;
+            double off = signed_pow_offset(norm(d), a.expo, div_px);
+            double dx = ((double)x + 0.5) + off;
+            dx = dx + sep_px;
+            double fl = floor(dx);
+            // keep the index sane for absurd parameters; such columns can never be on screen
+            int jc = (fl < -1.0e9) ? -1000000000 : ((fl > 1.0e9) ? 1000000000 : (int)fl);
+            dxs[x] = dx;
+            jcs[x] = jc;
+            int o = jc - x;
+            omin = min(omin, o); omax = max(omax, o);
+            lo = o; hi = o;
+        }
+        // a warp covers 32 consecutive source columns here: their offset range, for the per-destination windows below
+        for (int q = 16; q; q >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, q));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, q));
+        }
+        if ((threadIdx.x & 31) == 0) { bmin[x >> 5] = lo; bmax[x >> 5] = hi; }
     }
     for (int o = 16; o; o >>= 1) {
         omin = min(omin, __shfl_xor_sync(0xffffffffu, omin, o));
@@ -86,6 +100,13 @@ __global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
         // sources with jc in {j-1, j, j+1}:  x = jc - (jc - x)  lies in [j-1-omax, j+1-omin]
         long long lo = (long long)j - 1 - omax, hi = (long long)j + 1 - omin;
         int x0 = (int)max(lo, 0ll), x1 = (int)min(hi, (long long)w - 1);
+        if (x0 <= x1) {
+            // tighten with the offset range of the 32-column blocks the row-wide window touches
+            int lmin = 0x7FFFFFFF, lmax = (int)0x80000000;
+            for (int b = x0 >> 5; b <= (x1 >> 5); ++b) { lmin = min(lmin, bmin[b]); lmax = max(lmax, bmax[b]); }
+            x0 = max(x0, (int)max((long long)j - 1 - lmax, 0ll));
+            x1 = min(x1, (int)min((long long)j + 1 - lmin, (long long)w - 1));
+        }
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, ws = 0.0;   // float32-valued
         bool hit = false;
         for (int x = x0; x <= x1; ++x) {
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(256) k_hybrid_gapfill(const WarpArgs a, double
 }
 
 cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
-    size_t smem = (size_t)a.w * 12;
+    size_t smem = (size_t)a.w * 12 + (size_t)((a.w + 31) / 32) * 8 + 16;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_hybrid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_begin(K_HYBRID_SPLAT, s);
