@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             int kp = i0 - 1;
             if (kp < 0) bprev = -1;
             else if (kp >= npts) bprev = tw + 1;
-            else { float fx = floorf(px[sidx[kp]]); bprev = (fx < (float)t0) ? 0 : ((fx >= (float)(t0 + tw)) ? tw + 1 : (int)fx - t0 + 1); }
+            else bprev = min(max(__float2int_rd(px[sidx[kp]]) - t0 + 1, 0), tw + 1);
         }
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
@@ -682,10 +682,13 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 if (k < nsg) x1 = px[sp + 1];
                 const float pv = px[sp];
                 avv[e] = pv; spv[e] = sp;
-                float fx = floorf(pv);
-                int b = (fx < (float)t0) ? 0 : ((fx >= (float)(t0 + tw)) ? tw + 1 : (int)fx - t0 + 1);
-                for (int q = bprev + 1; q <= b; ++q) start[q] = k;
-                bprev = b;
+                // bucket = floor(x) - t0 + 1 clamped to [0, tw + 1] (the float -> int conversion saturates)
+                const int b = min(max(__float2int_rd(pv) - t0 + 1, 0), tw + 1);
+                if (b > bprev) {
+                    start[b] = k;
+                    for (int q = bprev + 1; q < b; ++q) start[q] = k;   // empty buckets in between (holes)
+                    bprev = b;
+                }
                 if (k == npts - 1) start[tw + 2] = npts;
             }
             x1v[e] = x1;
