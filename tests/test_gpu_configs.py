@@ -188,3 +188,13 @@ def test_one_process_multi_gpu_sharding(node, oracle):
         one = [o.numpy() for o in engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), prm, device=0)]
         for a, b in zip(got, one):
             assert np.array_equal(a, b)
+
+
+def test_4k_polylines_sharp_natural_tiles(node, oracle):
+    """3840 px rows do not fit one CTA's tables in sharp mode: the tiled kernel with its natural tile width serves
+    them (the 8K config test covers the same path at 7680 px; forced 64-px tiles are covered on every fixture)."""
+    img, dep = syn.make_image(1, 2160, 3840, seed=29), syn.make_depth(1, 2160, 3840, "scene", seed=29)
+    got, p = run(node, img, dep, fill_technique="Fill - Polylines Sharp", divergence=6.0, separation=-1.0)
+    want = oracle.node_generate(img, dep, **p)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(q8(g), q8(w_))
