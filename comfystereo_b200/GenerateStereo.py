@@ -41,15 +41,6 @@ def _gray_depth(depth_map, gpu_branch):
     raise ValueError(f"depth_map with {c} channels is not supported by this fill technique")
 
 
-def _resize_depth(depth, size):
-    """GS:141-148 / GS:214-220: bilinear, align_corners=False, applied to the GRAY depth."""
-    n, h, w, c = depth.shape
-    if c == 3:
-        depth = (0.2989 * depth[..., 0] + 0.5870 * depth[..., 1] + 0.1140 * depth[..., 2]).unsqueeze(-1)
-    d = torch.nn.functional.interpolate(depth.permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=False)
-    return d.permute(0, 2, 3, 1).contiguous()
-
-
 class StereoImageNode:
     @classmethod
     def INPUT_TYPES(cls):
@@ -104,16 +95,15 @@ class StereoImageNode:
         depth_map = depth_map.float() if depth_map.dtype != torch.float32 else depth_map
         if depth_map.dim() == 3:
             depth_map = depth_map.unsqueeze(-1)
+        # a depth batch of another size is resized on the GPU (gray first, then bilinear: GS:141-148, GS:214-220)
         depth = _gray_depth(depth_map, gpu_branch)
-        if tuple(depth.shape[1:3]) != tuple(image.shape[1:3]):
-            depth = _resize_depth(depth, tuple(image.shape[1:3]))
         group = min(int(batch_size), total) if gpu_branch else 0        # GS:119
         p = engine.make_params(key, modes, divergence, separation, stereo_balance, convergence_point,
                                stereo_offset_exponent, depth_map_blur, depth_blur_strength,
                                depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth,
                                group_size=group)
         if image.is_cuda:
-            outs = engine.stereo_batch_device(image, depth.to(image.device), p)
+            outs = engine.stereo_batch_device(image, depth.to(image.device), p, resize_depth=True)
             outs = tuple(o.cpu() for o in outs)
         else:
             if not torch.cuda.is_available():
@@ -124,9 +114,9 @@ class StereoImageNode:
                 (torch.distributed.is_available() and torch.distributed.is_initialized())
             ndev = 1 if single else torch.cuda.device_count()
             if ndev > 1 and total >= 2 * ndev:
-                outs = engine.stereo_batch_multi_gpu(image, depth, p, list(range(ndev)))
+                outs = engine.stereo_batch_multi_gpu(image, depth, p, list(range(ndev)), resize_depth=True)
             else:
-                outs = engine.stereo_batch_host(image, depth, p, device=torch.cuda.current_device())
+                outs = engine.stereo_batch_host(image, depth, p, device=torch.cuda.current_device(), resize_depth=True)
         pbar.update(total)
         return outs
 

@@ -29,7 +29,8 @@ class CsParams(ctypes.Structure):
         ("blur_enabled", ctypes.c_int32), ("blur_box", ctypes.c_int32),
         ("blur_radius", ctypes.c_int32), ("blur_vert_smooth", ctypes.c_int32),
         ("blur_edge_threshold", ctypes.c_double), ("blur_falloff", ctypes.c_double),
-        ("group_size", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("group_size", ctypes.c_int32), ("depth_h", ctypes.c_int32), ("depth_w", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "cs_output_dims": (_I, [_PP, _I, _I] + [ctypes.POINTER(_I)] * 4),
     "cs_workspace_bytes": (_SZ, [_PP, _I, _I, _I]),
     "cs_depth_prepare": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "cs_depth_resize": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cs_blur": (_I, [_P, _I, _I, _I, _PP, _P, _P, _P, _P, _P]),
     "cs_shift_indices": (_I, [_P, _I, _I, _I, _D, _D, _D, _I, _P, _P]),
     "cs_warp_fill": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _SZ, _P]),
@@ -88,7 +90,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        if handle.cs_abi_version() != 1:
+        if handle.cs_abi_version() != 2:
             raise ImportError("libcomfystereo_b200.so: ABI version mismatch, rebuild it")
         _lib = handle
     return _lib

@@ -22,7 +22,7 @@ static std::vector<ProfRec> g_prof;
 static std::atomic<int> g_prof_on{0};
 static const char* const kKernelNames[K_COUNT] = {
     "k_prepare", "k_edge_dist", "k_blur_blend", "k_depth_out", "k_warp_rows", "k_polylines", "k_polylines_exact",
-    "k_hybrid_splat", "k_hybrid_gapfill", "k_gpuwarp", "k_compose", "misc"};
+    "k_hybrid_splat", "k_hybrid_gapfill", "k_gpuwarp", "k_compose", "misc", "k_resize_gray"};
 void prof_begin(int id, cudaStream_t s) {
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     ProfRec r;
@@ -62,6 +62,8 @@ static int check_params(const cs_params* p) {
     if (!p) return fail(CS_ERR_ARG, "params is NULL");
     if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_HYBRID_EDGE_PLUS) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
     if (p->mode < CS_MODE_LEFT_RIGHT || p->mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
+    if (p->depth_h < 0 || p->depth_w < 0 || (p->depth_h > 0) != (p->depth_w > 0))
+        return fail(CS_ERR_ARG, "depth_h/depth_w must both be 0 or both be positive");
     if (p->blur_enabled) {
         if (p->blur_box < 1) return fail(CS_ERR_UNSUPPORTED, "kernel size should be greater than zero");
         if (p->blur_radius < 0 || p->blur_radius > kMaxBlurRadius)
@@ -94,8 +96,13 @@ static void eye_specs(const cs_params* p, int w, EyeSpec eye[2]) {
     }
 }
 
+static bool needs_resize(const cs_params* p, int h, int w) {
+    return p->depth_h > 0 && p->depth_w > 0 && (p->depth_h != h || p->depth_w != w);
+}
+
 struct Workspace {
     FrameStats* stats;
+    float* resized;      // N1: the gray depth at image size, only when the depth frames have another size
     float* gray;
     uint32_t* image_u8;
     float* blur_l;
@@ -114,6 +121,7 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return (char*)base + o; };
     ws.stats = (FrameStats*)take((size_t)chunk * sizeof(FrameStats));
+    if (needs_resize(p, h, w)) ws.resized = (float*)take(px * 4);
     ws.gray = (float*)take(px * 4);
     const bool cpu = is_cpu_technique(p->fill);
     if (cpu) ws.image_u8 = (uint32_t*)take(px * 4);
@@ -165,6 +173,12 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
     if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP)
         CS_CUDA(cudaMemsetAsync((char*)ws.warp_scratch + ws.warp_scratch_bytes - 16 * sizeof(int), 0, 16 * sizeof(int), s),
                 "memset status");
+    // N1 resize: depth frames of another size become a 1-channel gray depth at image size first
+    if (needs_resize(p, h, w)) {
+        CS_CUDA(launch_resize_gray(depth, n, p->depth_h, p->depth_w, c, h, w, ws.resized, s), "resize");
+        depth = ws.resized;
+        c = 1;
+    }
     // N1 + L1 (+ O1 input side for the CPU techniques)
     CS_CUDA(launch_prepare(cpu ? image : nullptr, depth, n, h, w, c, ws.gray, cpu ? ws.image_u8 : nullptr, ws.stats, s),
             "prepare");
@@ -292,6 +306,13 @@ int cs_depth_prepare(const float* depth, int n, int h, int w, int c, float* gray
     CS_CUDA(launch_prepare(nullptr, depth, n, h, w, c, gray, nullptr, st, s), "prepare");
     if (minmax) CS_CUDA(launch_export_stats(st, n, 0, minmax, 2, s), "export_stats");
     CS_CUDA(cudaFreeAsync(st, s), "cudaFreeAsync");
+    return CS_OK;
+}
+
+int cs_depth_resize(const float* depth, int n, int dh, int dw, int c, int h, int w, float* gray, void* stream) {
+    if (!depth || !gray || n < 1 || dh < 1 || dw < 1 || c < 1 || h < 1 || w < 1)
+        return fail(CS_ERR_ARG, "cs_depth_resize: bad argument");
+    CS_CUDA(launch_resize_gray(depth, n, dh, dw, c, h, w, gray, (cudaStream_t)stream), "resize");
     return CS_OK;
 }
 
@@ -436,7 +457,8 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
         const int m = (n - f0 < chunk) ? n - f0 : chunk;
         Workspace ws = carve(p, m, h, w, workspace);
         const size_t px = (size_t)h * w;
-        rc = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * px * c, m, h, w, c,
+        const size_t dpx = needs_resize(p, h, w) ? (size_t)p->depth_h * p->depth_w : px;
+        rc = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * dpx * c, m, h, w, c,
                        stereo + (size_t)f0 * ho * wo * 3, depth_l + (size_t)f0 * px * 3, depth_r + (size_t)f0 * px * 3,
                        mask + (size_t)f0 * hm * wm, ws, g_test_flags, s);
         if (rc) return rc;

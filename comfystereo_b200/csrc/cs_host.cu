@@ -153,7 +153,9 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};   // leave the caller's device as found
 
     const size_t px = (size_t)h * w;
-    const size_t b_img = px * 3 * 4, b_dep = px * c * 4, b_st = (size_t)ho * wo * 3 * 4, b_d = px * 3 * 4, b_m = (size_t)hm * wm * 4;
+    const bool resize = p->depth_h > 0 && p->depth_w > 0 && (p->depth_h != h || p->depth_w != w);
+    const size_t dpx = resize ? (size_t)p->depth_h * p->depth_w : px;   // depth frames may have their own size (N1)
+    const size_t b_img = px * 3 * 4, b_dep = dpx * c * 4, b_st = (size_t)ho * wo * 3 * 4, b_d = px * 3 * 4, b_m = (size_t)hm * wm * 4;
     const size_t in_frame = b_img + b_dep, out_frame = b_st + 2 * b_d + b_m;
     // chunk: whole GPU-Warp sub-batches (Q9); otherwise ~256 MB of I/O per slot
     int group = (p->fill == CS_FILL_GPU_WARP && p->group_size > 0) ? (p->group_size < n ? p->group_size : n) : 1;
@@ -175,7 +177,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     auto in_spans = [&](int f0, int m, char* slot, bool to_slot) {
         std::vector<Span> v;
         char* a = (char*)(image + (size_t)f0 * px * 3);
-        char* b = (char*)(depth + (size_t)f0 * px * c);
+        char* b = (char*)(depth + (size_t)f0 * dpx * c);
         if (to_slot) { v.push_back({slot, a, (size_t)m * b_img}); v.push_back({slot + (size_t)m * b_img, b, (size_t)m * b_dep}); }
         return v;
     };
@@ -210,7 +212,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
                 HOST_CUDA(cudaMemcpyAsync(din, cx.h_in[sl], (size_t)m * in_frame, cudaMemcpyHostToDevice, cx.s_in));
             } else {
                 HOST_CUDA(cudaMemcpyAsync(d_img, image + (size_t)f0 * px * 3, (size_t)m * b_img, cudaMemcpyHostToDevice, cx.s_in));
-                HOST_CUDA(cudaMemcpyAsync(d_dep, depth + (size_t)f0 * px * c, (size_t)m * b_dep, cudaMemcpyHostToDevice, cx.s_in));
+                HOST_CUDA(cudaMemcpyAsync(d_dep, depth + (size_t)f0 * dpx * c, (size_t)m * b_dep, cudaMemcpyHostToDevice, cx.s_in));
             }
             HOST_CUDA(cudaEventRecord(cx.ev_in[sl], cx.s_in));
             // kernels: need the upload, and the slot's device outputs must have left (chunk it-2)

@@ -146,11 +146,14 @@ struct WarpArgs {
 void count_launch();
 // Optional per-kernel timing (bench.py): CUDA events recorded on the launch stream around every kernel.
 enum KernelId { K_PREPARE = 0, K_EDGE_DIST, K_BLUR_BLEND, K_DEPTH_OUT, K_WARP_ROWS, K_POLY_FAST, K_POLY_EXACT,
-                K_HYBRID_SPLAT, K_HYBRID_GAPFILL, K_GPUWARP, K_COMPOSE, K_MISC, K_COUNT };
+                K_HYBRID_SPLAT, K_HYBRID_GAPFILL, K_GPUWARP, K_COMPOSE, K_MISC, K_RESIZE, K_COUNT };
 void prof_begin(int id, cudaStream_t s);
 void prof_end(int id, cudaStream_t s);
 int fail(int code, const char* fmt, ...);   // records the thread-local cs_last_error() text, returns code
 cudaError_t launch_init_stats(FrameStats* stats, int n, cudaStream_t s);
+// N1: gray + bilinear resize of a [n][dh][dw][c] depth to [n][h][w] (torch CPU arithmetic, strict float32)
+cudaError_t launch_resize_gray(const float* depth, int n, int dh, int dw, int c, int h, int w, float* out,
+                               cudaStream_t s);
 cudaError_t launch_prepare(const float* image, const float* depth, int n, int h, int w, int c,
                            float* gray, uint32_t* image_u8, FrameStats* stats, cudaStream_t s);
 // scale_mode 0: input already 0..255; 1: x255 when the frame's gray max <= 1 (SIG:1475);

@@ -35,6 +35,76 @@ __device__ __forceinline__ float gray_of(float r, float g, float b) {
     return s + e;
 }
 
+// ---- N1 depth resize: gray + F.interpolate(..., mode='bilinear', align_corners=False) (GS:141-148, GS:214-220) ----
+// torch's CPU kernel in strict float32 (no contraction; this file is built with -fmad=false):
+//   src = max(scale*(dst+0.5) - 0.5, 0), i0 = min(floor(src), in-1), i1 = i0 + (i0 < in-1), l1 = clamp(src - i0, 0, 1),
+//   l0 = 1 - l1; an axis whose size does not change maps to itself with weights (1, 0).
+//   out = (a00*lx0 + a01*lx1)*ly0 + (a10*lx0 + a11*lx1)*ly1, or torch's direct form for small outputs
+//   (h + w <= 128): ((ly0*lx0)*a00 + (ly0*lx1)*a01 + (ly1*lx0)*a10) + (ly1*lx1)*a11, summed left to right.
+struct ResizeAxis { int i0, i1; float l0, l1; };
+__device__ __forceinline__ ResizeAxis resize_axis(int d, int in, int out, float scale) {
+    ResizeAxis r;
+    if (in == out) { r.i0 = r.i1 = d; r.l0 = 1.0f; r.l1 = 0.0f; return r; }
+    float src = fmaxf(scale * ((float)d + 0.5f) - 0.5f, 0.0f);
+    int a = min((int)floorf(src), in - 1);
+    float lam = fminf(fmaxf(src - (float)a, 0.0f), 1.0f);
+    r.i0 = a;
+    r.i1 = a + (a < in - 1 ? 1 : 0);
+    r.l1 = lam;
+    r.l0 = 1.0f - lam;
+    return r;
+}
+
+template <int C>
+__device__ __forceinline__ float depth_tap(const float* __restrict__ p, int64_t i, int c_any) {
+    if (C == 3) return gray_of(__ldg(p + i * 3), __ldg(p + i * 3 + 1), __ldg(p + i * 3 + 2));
+    if (C == 1) return __ldg(p + i);
+    return __ldg(p + i * c_any);   // other channel counts: channel 0 (GS:138)
+}
+
+// One thread = one output pixel; the source frame (smaller or similar size) is served by L1/L2.
+template <int C>
+__global__ void __launch_bounds__(256) k_resize_gray(const float* __restrict__ depth, int c_any, int dh, int dw,
+                                                     int h, int w, float sy, float sx, int direct,
+                                                     float* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int cc = (C > 0) ? C : c_any;
+    if (x >= w) return;
+    const float* src = depth + (int64_t)blockIdx.z * dh * dw * cc;
+    const ResizeAxis ay = resize_axis(y, dh, h, sy), ax = resize_axis(x, dw, w, sx);
+    const float a00 = depth_tap<C>(src, (int64_t)ay.i0 * dw + ax.i0, c_any);
+    const float a01 = depth_tap<C>(src, (int64_t)ay.i0 * dw + ax.i1, c_any);
+    const float a10 = depth_tap<C>(src, (int64_t)ay.i1 * dw + ax.i0, c_any);
+    const float a11 = depth_tap<C>(src, (int64_t)ay.i1 * dw + ax.i1, c_any);
+    float v;
+    if (direct) {
+        const float w00 = ay.l0 * ax.l0, w01 = ay.l0 * ax.l1, w10 = ay.l1 * ax.l0, w11 = ay.l1 * ax.l1;
+        float acc = w00 * a00 + w01 * a01;
+        acc = acc + w10 * a10;
+        v = acc + w11 * a11;
+    } else {
+        const float top = a00 * ax.l0 + a01 * ax.l1;
+        const float bot = a10 * ax.l0 + a11 * ax.l1;
+        v = top * ay.l0 + bot * ay.l1;
+    }
+    out[((int64_t)blockIdx.z * h + y) * w + x] = v;
+}
+
+cudaError_t launch_resize_gray(const float* depth, int n, int dh, int dw, int c, int h, int w, float* out,
+                               cudaStream_t s) {
+    const float sy = (float)dh / (float)h, sx = (float)dw / (float)w;   // area_pixel_compute_scale, float32
+    const int direct = (h + w <= 128) ? 1 : 0;
+    dim3 grid((w + 255) / 256, h, n);
+    prof_begin(K_RESIZE, s);
+    if (c == 3) k_resize_gray<3><<<grid, 256, 0, s>>>(depth, c, dh, dw, h, w, sy, sx, direct, out);
+    else if (c == 1) k_resize_gray<1><<<grid, 256, 0, s>>>(depth, c, dh, dw, h, w, sy, sx, direct, out);
+    else k_resize_gray<0><<<grid, 256, 0, s>>>(depth, c, dh, dw, h, w, sy, sx, direct, out);
+    prof_end(K_RESIZE, s);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // clip(x*255, 0, 255).astype(uint8): truncation, NaN -> 0 (SIG:1508)
 __device__ __forceinline__ int quant_u8(float x) {
     float v = x * 255.0f;

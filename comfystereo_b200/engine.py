@@ -102,10 +102,24 @@ def default_chunk(p, n, h, w):
     return min(chunk, n)
 
 
-def stereo_batch_device(image, depth, p, out=None, chunk=None):
+def _depth_geometry(p, depth, n, h, w, resize_depth):
+    """Checks the depth batch against the image batch.  Frames of another size are an error for the function
+    API (SIG:1586) and are resized on the GPU for the node (GS:141-148, GS:214-220): returns the params to use."""
+    if depth.shape[0] != n:
+        raise AssertionError('Depthmap and the image must have the same number of frames')
+    if tuple(depth.shape[1:3]) == (h, w):
+        return p
+    if not resize_depth:
+        raise AssertionError('Depthmap and the image must have the same size')
+    q = CsParams.from_buffer_copy(p)
+    q.depth_h, q.depth_w = int(depth.shape[1]), int(depth.shape[2])
+    return q
+
+
+def stereo_batch_device(image, depth, p, out=None, chunk=None, resize_depth=False):
     """The hot path on device-resident tensors.
 
-    image [N,H,W,3] float32 cuda, depth [N,H,W,C] float32 cuda (same H,W).
+    image [N,H,W,3] float32 cuda, depth [N,H,W,C] float32 cuda (same H,W; or [N,Hd,Wd,C] with resize_depth=True).
     Returns (stereo, depth_left, depth_right, mask) cuda tensors in the node's layouts.
     Asynchronous on the current stream."""
     if not (image.is_cuda and depth.is_cuda):
@@ -119,8 +133,7 @@ def stereo_batch_device(image, depth, p, out=None, chunk=None):
         raise ValueError("image must have 3 channels")
     if depth.dim() == 3:
         depth = depth.unsqueeze(-1)
-    if depth.shape[:3] != (n, h, w):
-        raise AssertionError('Depthmap and the image must have the same size')
+    p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     lib = _lib.lib()
     dev = image.device
@@ -157,7 +170,7 @@ def _out_bytes(s_shape, d_shape, m_shape):
     return total
 
 
-def stereo_batch_host(image, depth, p, device=0, pin_outputs=True):
+def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=False):
     """The hot path on CPU tensors (what ComfyUI hands the node): chunks are streamed through the
     GPU with upload, kernels and download overlapped inside the library.  Returns CPU tensors."""
     if image.is_cuda or depth.is_cuda:
@@ -169,8 +182,7 @@ def stereo_batch_host(image, depth, p, device=0, pin_outputs=True):
         raise ValueError("image must have 3 channels")
     if depth.dim() == 3:
         depth = depth.unsqueeze(-1)
-    if depth.shape[:3] != (n, h, w):
-        raise AssertionError('Depthmap and the image must have the same size')
+    p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
     pin = bool(pin_outputs) and torch.cuda.is_available() and _out_bytes(s_shape, d_shape, m_shape) <= PIN_LIMIT_BYTES
@@ -200,7 +212,7 @@ def group_aligned_shard_range(n, rank, world, group):
     return min(glo * group, n), min(ghi * group, n)
 
 
-def stereo_batch_multi_gpu(image, depth, p, devices):
+def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False):
     """Frame-sharded run over several GPUs of one box from ONE process (used by the node when more
     than one device is visible).  No collective: every device streams its contiguous frame range
     and writes straight into its slice of the (pinned) host outputs, which is in-order assembly by
@@ -210,6 +222,7 @@ def stereo_batch_multi_gpu(image, depth, p, devices):
         depth = depth.unsqueeze(-1)
     image = image.contiguous().float()
     depth = depth.contiguous().float()
+    p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
     pin = torch.cuda.is_available() and _out_bytes(s_shape, d_shape, m_shape) <= PIN_LIMIT_BYTES

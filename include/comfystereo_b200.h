@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 1
+#define CS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CS_API __attribute__((visibility("default")))
@@ -91,6 +91,8 @@ typedef struct cs_params {
     double blur_falloff;
     int32_t group_size;         /* GPU Warp only: frames per reference sub-batch (batch_size, GS:119);
                                    the "is depth 0..1 or 0..255" tests are sub-batch wide (SIG:1045, 315, 1125) */
+    int32_t depth_h;            /* size of the depth frames when it differs from the image's (GS:141-148, GS:214-220): */
+    int32_t depth_w;            /* the gray depth is resized bilinearly (align_corners=False) first; 0 = same as the image */
     int32_t reserved;
 } cs_params;
 
@@ -113,6 +115,13 @@ CS_API size_t cs_workspace_bytes(const cs_params *p, int chunk, int h, int w);
  * SIG:1475 / SIG:1045 / SIG:1587-1588 need.  gray [n][h][w]; minmax [n][2] = {min, max}. */
 CS_API int cs_depth_prepare(const float *depth, int n, int h, int w, int c, float *gray, float *minmax,
                      void *stream);
+
+/* N1 resize.  Replaces the gray conversion + torch.nn.functional.interpolate(gray, size=(h, w),
+ * mode='bilinear', align_corners=False) of GS:132-148 / GS:206-220 for a depth batch whose frames are
+ * dh x dw: depth [n][dh][dw][c] -> gray [n][h][w].  Arithmetic: torch's CPU kernel in strict float32
+ * (see cs_prep.cu); c == 3 is converted to gray per tap, other channel counts use channel 0. */
+CS_API int cs_depth_resize(const float *depth, int n, int dh, int dw, int c, int h, int w, float *gray,
+                    void *stream);
 
 /* B1.  Replaces directional_motion_blur_gpu(depth, s, thr, s, falloff, vert), SIG:1171-1251.
  * depth255 [n][h][w] is on the 0..255 scale; writes blur_l / blur_r [n][h][w] and, if minmax

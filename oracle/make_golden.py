@@ -109,8 +109,8 @@ def crc(*arrays):
 
 def case_inputs(spec):
     img = syn.make_image(spec["n"], spec["h"], spec["w"], seed=spec["seed"], black_box=spec["black_box"])
-    dep = syn.make_depth(spec["n"], spec["h"], spec["w"], spec["kind"], seed=spec["seed"],
-                         channels=spec["channels"], scale255=spec["scale255"])
+    dep = syn.make_depth(spec["n"], spec.get("dh", spec["h"]), spec.get("dw", spec["w"]), spec["kind"],
+                         seed=spec["seed"], channels=spec["channels"], scale255=spec["scale255"])
     return img, dep
 
 
@@ -218,6 +218,99 @@ def main_post():
     print("post-fill stage cases:", len(stage_cases_post()))
 
 
+# ---- N1 depth resize (GS:141-148 / GS:214-220) ---------------------------------------------------
+# torch's CPU bilinear kernel contracts multiply-adds into FMAs in its AVX2/AVX512 builds (which ones
+# depends on the tensor shape), so the reference's resized depth differs between machines by ~1 ulp of
+# the source coordinate.  The fixtures are generated with ATEN_CPU_CAPABILITY=default (strict float32,
+# what the oracle restates bit-exactly); `out_native` keeps this machine's default-dispatch result to
+# bound the difference.
+RESIZE_SHAPES = [(37, 53, 74, 106), (37, 53, 100, 91), (64, 64, 48, 40), (11, 7, 5, 3), (20, 30, 20, 45),
+                 (30, 20, 45, 20), (96, 128, 48, 64), (1, 9, 4, 31), (9, 1, 31, 4), (135, 240, 270, 480)]
+
+
+def resize_specs():
+    kinds = ["scene", "noise", "card", "steps"]
+    return [dict(name=f"{i:03d}", dh=dh, dw=dw, h=h, w=w, kind=kinds[i % len(kinds)], seed=300 + i)
+            for i, (dh, dw, h, w) in enumerate(RESIZE_SHAPES)]
+
+
+def node_resize_cases():
+    def case(name, n, dh, dw, h, w, kind, channels, **params):
+        p = dict(DEFAULTS)
+        p.update(params)
+        return dict(name=name, n=n, h=h, w=w, dh=dh, dw=dw, kind=kind, seed=400 + len(name), channels=channels,
+                    scale255=False, black_box=False, params=p)
+    return [
+        case("rs_gw_up", 3, 20, 30, 48, 64, "scene", 3, fill_technique='GPU Warp (Fast)', depth_map_blur=False, batch_size=2),
+        case("rs_gw_blur", 2, 27, 35, 48, 64, "scene", 1, fill_technique='GPU Warp (Fast)', depth_blur_strength=7.0),
+        case("rs_naive_down", 2, 96, 128, 48, 64, "noise", 1, fill_technique='Fill - Naive', depth_map_blur=False),
+        case("rs_sharp_up", 2, 37, 53, 64, 96, "scene", 3, fill_technique='Fill - Polylines Sharp', depth_map_blur=False),
+        case("rs_soft_blur", 1, 37, 53, 64, 96, "scene", 3, fill_technique='Fill - Polylines Soft', depth_blur_strength=7.0,
+             modes="top-bottom"),
+        case("rs_hybrid_wide", 1, 48, 40, 48, 64, "card", 3, fill_technique='Imperfect fill - Hybrid Edge',
+             depth_map_blur=False, modes="red-cyan-anaglyph"),
+    ]
+
+
+def _interp(gray, size):
+    return torch.nn.functional.interpolate(torch.from_numpy(gray)[None, None], size=size, mode='bilinear',
+                                           align_corners=False)[0, 0].numpy()
+
+
+def main_resize():
+    """python oracle/make_golden.py resize -- appends the depth-resize fixtures (stage + node) to the manifest."""
+    assert ref_loader.reference_available(), "needs /root/reference"
+    import subprocess
+    import tempfile
+    if os.environ.get("ATEN_CPU_CAPABILITY") != "default":
+        # pass 1 (this machine's dispatch): the native results, then re-run strictly
+        tmp = tempfile.mkdtemp()
+        native = {}
+        for spec in resize_specs():
+            d = syn.make_depth(1, spec["dh"], spec["dw"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0]
+            native[spec["name"]] = _interp(d, (spec["h"], spec["w"]))
+        np.savez(os.path.join(tmp, "native.npz"), **native)
+        env = dict(os.environ, ATEN_CPU_CAPABILITY="default", CS_NATIVE_NPZ=os.path.join(tmp, "native.npz"))
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "resize"], env=env)
+        return
+    assert torch.backends.cpu.get_cpu_capability() == "DEFAULT"
+    native = np.load(os.environ["CS_NATIVE_NPZ"])
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    manifest["resize"] = []
+    for spec in resize_specs():
+        d = syn.make_depth(1, spec["dh"], spec["dw"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0]
+        np.savez_compressed(os.path.join(GOLDEN, f"resize_{spec['name']}.npz"), crc=crc(d),
+                            out_strict=_interp(d, (spec["h"], spec["w"])), out_native=native[spec["name"]])
+        manifest["resize"].append(spec)
+    manifest["node"] = [s for s in manifest["node"] if not s["name"].startswith("rs_")]
+    for spec in node_resize_cases():
+        img, dep, outs, blur = run_node(spec)
+        np.savez_compressed(os.path.join(GOLDEN, f"node_{spec['name']}.npz"), **node_record(spec, img, dep, outs, blur))
+        manifest["node"].append(spec)
+        print("node", spec["name"], [o.shape for o in outs])
+    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+    print("resize cases:", len(manifest["resize"]), "+", len(node_resize_cases()), "node cases")
+
+
+def node_record(spec, img, dep, outs, blur):
+    is_gw = spec["params"]["fill_technique"] == 'GPU Warp (Fast)'
+    stereo, dl, dr, mask = outs
+    rec = dict(crc=crc(img, dep))
+    if is_gw:
+        rec.update(stereo=stereo.astype(np.float32), depth_l=dl[..., 0].astype(np.float32),
+                   depth_r=dr[..., 0].astype(np.float32), mask=(mask > 0).astype(np.uint8))
+    else:
+        q = lambda a: np.rint(a * 255.0).astype(np.uint8)
+        assert np.array_equal(q(stereo).astype(np.float32) / np.float32(255), stereo)
+        rec.update(stereo=q(stereo), depth_l=q(dl[..., 0]), depth_r=q(dr[..., 0]), mask=q(mask))
+        assert np.array_equal(dl[..., 0], dl[..., 1]) and np.array_equal(dl[..., 0], dl[..., 2])
+    if blur is not None:
+        rec.update(blur_l=blur[0], blur_r=blur[1])
+    return rec
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -253,5 +346,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "post":
         main_post()
+    elif len(sys.argv) > 1 and sys.argv[1] == "resize":
+        main_resize()
     else:
         main()

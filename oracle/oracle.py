@@ -72,6 +72,18 @@ def gray3(rgb):
     return out
 
 
+def resize_bilinear(gray, size):
+    """N1 (GS:141-148 / GS:214-220): F.interpolate(gray[None, None], size, 'bilinear', align_corners=False) on a
+    [H,W] or [N,H,W] float32 array, strict float32 arithmetic (see stereo_oracle.c)."""
+    g = _c(gray, np.float32)
+    if g.ndim == 3:
+        return np.stack([resize_bilinear(f, size) for f in g])
+    oh, ow = int(size[0]), int(size[1])
+    out = np.empty((oh, ow), np.float32)
+    lib().orc_resize_bilinear(_p(g), g.shape[0], g.shape[1], oh, ow, _p(out))
+    return out
+
+
 def py_round_half_even(x):
     return int(round(float(x)))  # python round() == banker's rounding, SIG:1208 (Q11)
 
@@ -372,6 +384,8 @@ def node_generate(image, depth_map, divergence=4.5, separation=0.0, modes="left-
                 dm = gray3(dm)
             else:
                 dm = dm[..., 0]
+            if dm.shape[1:] != img.shape[2:]:                      # GS:141-148
+                dm = resize_bilinear(dm, img.shape[2:])
             res, dl, dr, mask = create_stereoimages_gpu(
                 img, dm, divergence, separation, [modes], stereo_balance, stereo_offset_exponent,
                 convergence_point, depth_blur_strength, depth_blur_edge_threshold, depth_map_blur,
@@ -385,6 +399,8 @@ def node_generate(image, depth_map, divergence=4.5, separation=0.0, modes="left-
         for i in range(N):
             dm = depth_map[i]
             dm = gray3(dm) if dm.shape[2] == 3 else dm[..., 0]
+            if dm.shape != image[i].shape[:2]:                    # GS:214-220
+                dm = resize_bilinear(dm, image[i].shape[:2])
             res, ml, mr = create_stereoimages(
                 image[i].transpose(2, 0, 1), dm, divergence, separation, [modes], stereo_balance,
                 stereo_offset_exponent, key, depth_blur_strength, depth_blur_edge_threshold,

@@ -48,6 +48,18 @@ def blur(d255, strength, thr, falloff, vert):
     return (L[0], R[0], mm.cpu().numpy()) if single else (L, R, mm.cpu().numpy())
 
 
+def depth_resize(depth, size):
+    """cs_depth_resize: depth [n,dh,dw,c] float32 -> gray [n,h,w] at size=(h,w)."""
+    d = np.ascontiguousarray(depth, np.float32)
+    n, dh, dw, c = d.shape
+    h, w = int(size[0]), int(size[1])
+    t = torch.from_numpy(d).to(dev())
+    out = torch.empty((n, h, w), dtype=torch.float32, device=dev())
+    _lib.check(_lib.lib().cs_depth_resize(t.data_ptr(), n, dh, dw, c, h, w, out.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
 def warp_fill(img_u8, depth, fill_key, divergence, separation, expo, conv, exact=False, flags=0):
     """cs_warp_fill on ONE eye: img_u8 [n,h,w,3] or [h,w,3], depth same leading dims.  Returns uint8 [...,4]
     (RGB + the filled/mask flag byte)."""

@@ -121,11 +121,44 @@ def test_compose_modes(gu, oracle):
         assert np.array_equal(mk, (ref.astype(np.int32).sum(-1) == 0).astype(np.float32))
 
 
+# ------------------------------------------------------------------------------------------ N1 resize
+@pytest.mark.parametrize("spec", MAN["resize"], ids=[s["name"] for s in MAN["resize"]])
+def test_depth_resize_vs_reference(gu, oracle, spec):
+    """gray + bilinear resize (GS:141-148 / GS:214-220): bit-exact against torch's strict CPU kernel (fixture) and the
+    oracle; torch's FMA-contracting builds (out_native) stay within 1e-4."""
+    g = load_golden("resize", spec["name"])
+    d = syn.make_depth(1, spec["dh"], spec["dw"], spec["kind"], seed=spec["seed"], channels=1)
+    got = gu.depth_resize(d, (spec["h"], spec["w"]))[0]
+    assert np.array_equal(got, g["out_strict"])
+    assert np.array_equal(got, oracle.resize_bilinear(d[0, ..., 0], (spec["h"], spec["w"])))
+    assert np.abs(got - g["out_native"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 53, 3, 80, 120), (2, 64, 64, 1, 64, 64), (2, 270, 480, 3, 1080, 1920),
+                                   (1, 1080, 1920, 1, 405, 721), (2, 9, 13, 4, 33, 95), (1, 518, 924, 3, 1080, 1920)])
+def test_depth_resize_vs_oracle(gu, oracle, shape):
+    """Batches, 1 / 3 / other channel counts (gray per tap; channel 0 for other counts, GS:138), both of torch's
+    arithmetic forms (direct for h + w <= 128), up- and down-scaling, 0..255 values: bit-exact."""
+    n, dh, dw, c, h, w = shape
+    rng = np.random.default_rng(sum(shape))
+    d = (rng.random((n, dh, dw, c), dtype=np.float32) * np.float32(255 if c == 1 else 1)).astype(np.float32)
+    gray = oracle.gray3(d) if c == 3 else d[..., 0]
+    want = oracle.resize_bilinear(gray, (h, w))
+    assert np.array_equal(gu.depth_resize(d, (h, w)), want)
+
+
+def test_function_api_rejects_mismatched_depth(gu):
+    """create_stereoimages asserts equal sizes (SIG:1586); only the node resizes."""
+    from comfystereo_b200 import stereoimage_generation as sig
+    with pytest.raises(AssertionError, match="same size"):
+        sig.create_stereoimages(torch.rand(3, 16, 24), torch.rand(8, 12), 3.0)
+
+
 # ------------------------------------------------------------------------------------------ node
 def _node_inputs(spec):
     img = syn.make_image(spec["n"], spec["h"], spec["w"], seed=spec["seed"], black_box=spec["black_box"])
-    dep = syn.make_depth(spec["n"], spec["h"], spec["w"], spec["kind"], seed=spec["seed"],
-                         channels=spec["channels"], scale255=spec["scale255"])
+    dep = syn.make_depth(spec["n"], spec.get("dh", spec["h"]), spec.get("dw", spec["w"]), spec["kind"],
+                         seed=spec["seed"], channels=spec["channels"], scale255=spec["scale255"])
     return img, dep
 
 
@@ -283,6 +316,34 @@ def test_device_path_equals_host_path(gu, node):
                                          chunk=(group if group else 1))
         for a, b, c in zip(host, devo, one):
             assert torch.equal(a, b.cpu()) and torch.equal(a, c.cpu())
+
+
+def test_resized_depth_device_host_and_chunks_agree(gu, oracle, node):
+    """Depth frames of another size: host path (several chunks), device path and one-frame chunks give the same
+    bytes, equal to the oracle's node on the same inputs; a 540p depth drives a 1080p image."""
+    from comfystereo_b200 import engine
+    img = syn.make_image(5, 40, 96, seed=12)
+    dep = syn.make_depth(5, 25, 61, "scene", seed=12)
+    for key, group in (("naive", 0), ("gpu_warp", 2)):
+        p = engine.make_params(key, "left-right", 9.0, 0.5, 0.1, 0.5, 2.0, True, 7.0, 20.0, 2.0, 3, group_size=group)
+        host = engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), p, device=0, resize_depth=True)
+        devo = engine.stereo_batch_device(torch.from_numpy(img).cuda(), torch.from_numpy(dep).cuda(), p,
+                                          resize_depth=True)
+        one = engine.stereo_batch_device(torch.from_numpy(img).cuda(), torch.from_numpy(dep).cuda(), p,
+                                         chunk=(group if group else 1), resize_depth=True)
+        for a, b, c in zip(host, devo, one):
+            assert torch.equal(a, b.cpu()) and torch.equal(a, c.cpu())
+        with pytest.raises(AssertionError, match="same size"):
+            engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), p, device=0)
+    img = syn.make_image(2, 1080, 1920, seed=13)
+    dep = syn.make_depth(2, 540, 960, "scene", seed=13, channels=1)
+    kw = dict(divergence=3.5, separation=0.0, modes="left-right", stereo_balance=0.0, convergence_point=0.5,
+              stereo_offset_exponent=2.0, fill_technique="Fill - Polylines Sharp", depth_blur_edge_threshold=20.0,
+              depth_blur_strength=20.0, depth_map_blur=True, depth_blur_falloff=2.0, depth_blur_vert_smooth=6)
+    got = [o.numpy() for o in node.generate(torch.from_numpy(img), torch.from_numpy(dep), **kw)]
+    want = oracle.node_generate(img, dep, **kw)
+    for a, b in zip(got, want):
+        assert np.array_equal(gu.q8(a), gu.q8(b))
 
 
 def test_errors_match_reference(gu, node):

@@ -29,8 +29,8 @@ def _crc(*arrays):
 
 def _node_inputs(spec):
     img = syn.make_image(spec["n"], spec["h"], spec["w"], seed=spec["seed"], black_box=spec["black_box"])
-    dep = syn.make_depth(spec["n"], spec["h"], spec["w"], spec["kind"], seed=spec["seed"],
-                         channels=spec["channels"], scale255=spec["scale255"])
+    dep = syn.make_depth(spec["n"], spec.get("dh", spec["h"]), spec.get("dw", spec["w"]), spec["kind"],
+                         seed=spec["seed"], channels=spec["channels"], scale255=spec["scale255"])
     return img, dep
 
 
@@ -59,6 +59,18 @@ def test_stage_vs_reference(oracle, spec):
         warped, mask = oracle.gpuwarp_eye(chw, d, spec["div_px"], spec["sep_px"], spec["expo"], spec["conv"])
         assert np.array_equal(mask.astype(np.uint8), g["mask"])
         assert np.abs(warped - g["warped"]).max() <= 2e-5
+
+
+@pytest.mark.parametrize("spec", MAN["resize"], ids=[s["name"] for s in MAN["resize"]])
+def test_resize_vs_reference(oracle, spec):
+    """N1 depth resize (GS:141-148 / GS:214-220): bit-exact against torch's strict (ATEN_CPU_CAPABILITY=default)
+    kernel; torch's FMA-contracting AVX builds stay within ~1 ulp of the source coordinate of it."""
+    g = load_golden("resize", spec["name"])
+    d = syn.make_depth(1, spec["dh"], spec["dw"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0]
+    assert _crc(d) == int(g["crc"])
+    out = oracle.resize_bilinear(d, (spec["h"], spec["w"]))
+    assert np.array_equal(out, g["out_strict"])
+    assert np.abs(out - g["out_native"]).max() <= 1e-4
 
 
 @pytest.mark.parametrize("spec", MAN["node"], ids=[s["name"] for s in MAN["node"]])
