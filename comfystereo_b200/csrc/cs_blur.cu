@@ -127,17 +127,23 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
     }
 }
 
+// trunc(t) mod 256 as numpy's float32 -> int64 -> uint8 cast chain does it (wrap quirk Q1).  Beyond the int32 range a
+// float32 is a multiple of 256 (24-bit significand), and NaN / overflow convert to INT64_MIN on x86: all of them give 0.
+__device__ __forceinline__ int wrap_u8(float t) {
+    return (fabsf(t) < 2147483520.0f) ? (__float2int_rz(t) & 255) : 0;
+}
+
 // ------------------------------------------------------------------------------------ blend
 constexpr int kSeg = 256;  // pixels per row segment = threads per CTA
 constexpr int kTileY = 8;  // rows per work item
 constexpr int kRowPad = 16;
 
-// Work item = kTileY rows x kSeg columns, staged once in shared memory: the LUT weights of the kTileY + 2v rows the
-// vertical box touches, and the kTileY depth row segments with the horizontal box's halo.
-//   pass 1  thread = column: one walk down the staged weight rows feeds all kTileY vertical sums (each weight is
-//           loaded once and used by up to 2v+1 accumulators; every accumulator still sees its taps in ascending order)
-//   pass 2  thread = (row, 8 consecutive columns): the bs-tap horizontal box for 8 pixels from a register window
-//           (15 loads per 64 fused multiply-adds), blend, min/max, depth outputs
+// Work item = kTileY rows x kSeg columns:
+//   pass 1  thread = column: loads the kTileY + 2v edge distances of its column, looks their weights up and feeds all
+//           kTileY vertical sums from registers (each weight is used by up to 2v+1 accumulators; every accumulator still
+//           sees its taps in ascending order); the sums go to shared memory for pass 2
+//   pass 2  thread = (row, 8 consecutive columns): the bs-tap horizontal box for 8 pixels from a register window over
+//           the depth rows staged with their halo (15 loads per 64 fused multiply-adds), blend, min/max, depth outputs
 // Rows outside the image hold weight 0: fmaf(0, wv, acc) == acc, which is the reference's zero padding.
 // Tap order (ascending, fmaf) is the oracle's, so the result is bit-identical to it.
 template <int V>   // vertical smoothing radius (0..15): compile-time so that the column walk unrolls without predicates
@@ -151,13 +157,16 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
     constexpr int v = V;
     constexpr int wrows = kTileY + 2 * V;
     const int rw = (kSeg + bs + kRowPad + 3) & ~3;     // row pitch, multiple of 4 floats
-    float* s_wl = s_dyn;                         // [wrows][kSeg]   later: [kTileY][kSeg] vertical sums, then outputs
-    float* s_wr = s_wl + wrows * kSeg;           // [wrows][kSeg]
-    float* s_row = s_wr + wrows * kSeg;          // [kTileY][rw]
+    float* s_wl = s_dyn;                         // [kTileY][kSeg] vertical sums of the weights, then the depth outputs
+    float* s_wr = s_wl + kTileY * kSeg;          // [kTileY][kSeg]
+    float* s_row = s_wr + kTileY * kSeg;         // [kTileY][rw]
     __shared__ float s_red[4][kSeg / 32];
-    __shared__ float s_lut[256];
+    __shared__ float s_lut[257];
+    __shared__ float s_q[256];                   // k / 255.0f, the depth outputs' dequantisation (GS:365)
     const int tid = threadIdx.x;
     s_lut[tid] = lut.w[tid];
+    s_q[tid] = (float)tid / 255.0f;
+    if (tid == 0) s_lut[256] = 0.0f;
     const int frame = blockIdx.y;
     const float scale = frame_scale(st, frame, scale_mode, group, n);
     const float wv = 1.0f / (float)(2 * v + 1);
@@ -179,27 +188,53 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
         const int ty = item / segs_per_row, x0 = (item - ty * segs_per_row) * kSeg;
         const int y0 = ty * kTileY;
         const int x = x0 + tid;
-        // ---- stage the weights of rows y0 - v .. y0 + kTileY - 1 + v (all byte loads first, then the LUT gathers)
+        // ---- pass 1: vertical sums of column tid for all kTileY rows, straight from registers: the thread that
+        // loads a column's distances (rows y0 - v .. y0 + kTileY - 1 + v, all byte loads first) is the one that sums them
+        float al[kTileY], ar[kTileY];
         {
             uint32_t da[wrows], db[wrows];
             const bool xin = x < w;
+            if (y0 - v >= 0 && y0 + kTileY + v <= h) {      // interior tile (CTA-uniform): no per-row tests
+                const uint8_t* pa = dl + (int64_t)(y0 - v) * w + (xin ? x : 0);
+                const uint8_t* pb = dr + (int64_t)(y0 - v) * w + (xin ? x : 0);
 #pragma unroll
-            for (int rr = 0; rr < wrows; ++rr) {
-                const int yy = y0 - v + rr;
-                const bool in = xin && yy >= 0 && yy < h;
-                const int off = in ? yy * w + x : 0;
-                da[rr] = in ? (uint32_t)dl[off] : 256u;
-                db[rr] = in ? (uint32_t)dr[off] : 256u;
+                for (int rr = 0; rr < wrows; ++rr) {
+                    da[rr] = *pa; db[rr] = *pb;
+                    pa += w; pb += w;
+                }
+                if (!xin) {
+#pragma unroll
+                    for (int rr = 0; rr < wrows; ++rr) { da[rr] = 256u; db[rr] = 256u; }
+                }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < wrows; ++rr) {
+                    const int yy = y0 - v + rr;
+                    const bool in = xin && yy >= 0 && yy < h;
+                    const int off = in ? yy * w + x : 0;
+                    da[rr] = in ? (uint32_t)dl[off] : 256u;     // s_lut[256] = 0: rows outside the image weigh nothing
+                    db[rr] = in ? (uint32_t)dr[off] : 256u;
+                }
             }
 #pragma unroll
-            for (int rr = 0; rr < wrows; ++rr) {
-                s_wl[rr * kSeg + tid] = (da[rr] < 256u) ? s_lut[da[rr]] : 0.0f;
-                s_wr[rr * kSeg + tid] = (db[rr] < 256u) ? s_lut[db[rr]] : 0.0f;
+            for (int r = 0; r < kTileY; ++r) { al[r] = 0.0f; ar[r] = 0.0f; }
+#pragma unroll
+            for (int t = 0; t < wrows; ++t) {
+                const float a = s_lut[da[t]], b = s_lut[db[t]];
+                if (v > 0) {
+#pragma unroll
+                    for (int r = 0; r < kTileY; ++r) {
+                        const int tap = t - r;
+                        if (tap >= 0 && tap <= 2 * v) { al[r] = fmaf(a, wv, al[r]); ar[r] = fmaf(b, wv, ar[r]); }
+                    }
+                } else {
+                    al[t] = a; ar[t] = b;
+                }
             }
         }
         // ---- stage depth[y][x0 - lo .. ) for the tile's rows (zeros outside the row)
-        for (int i = tid; i < rw; i += kSeg) {
-            const int xx = x0 - lo + i;
+        {
+            const int xx = x0 - lo + tid;                 // body: thread = column, all kTileY rows
             const bool xin2 = xx >= 0 && xx < w;
             float tmp[kTileY];
 #pragma unroll
@@ -208,28 +243,14 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
                 tmp[r] = (xin2 && y < h) ? base[(int64_t)y * w + xx] : 0.0f;
             }
 #pragma unroll
-            for (int r = 0; r < kTileY; ++r) s_row[r * rw + i] = scaled(tmp[r], scale);
-        }
-        __syncthreads();
-        // ---- pass 1: vertical sums of column tid for all kTileY rows
-        float al[kTileY], ar[kTileY];
-        if (v > 0) {
-#pragma unroll
-            for (int r = 0; r < kTileY; ++r) { al[r] = 0.0f; ar[r] = 0.0f; }
-#pragma unroll
-            for (int t = 0; t < wrows; ++t) {
-                const float a = s_wl[t * kSeg + tid], b = s_wr[t * kSeg + tid];
-#pragma unroll
-                for (int r = 0; r < kTileY; ++r) {
-                    const int tap = t - r;
-                    if (tap >= 0 && tap <= 2 * v) { al[r] = fmaf(a, wv, al[r]); ar[r] = fmaf(b, wv, ar[r]); }
-                }
+            for (int r = 0; r < kTileY; ++r) s_row[r * rw + tid] = scaled(tmp[r], scale);
+            // halo (the bs - 1 columns past the segment that the box reaches): warp = row, lane = column
+            const int y = y0 + pr;
+            for (int i = kSeg + pg; i < kSeg + bs - 1; i += 32) {
+                const int xh = x0 - lo + i;
+                s_row[pr * rw + i] = (xh >= 0 && xh < w && y < h) ? scaled(base[(int64_t)y * w + xh], scale) : 0.0f;
             }
-        } else {
-#pragma unroll
-            for (int r = 0; r < kTileY; ++r) { al[r] = s_wl[r * kSeg + tid]; ar[r] = s_wr[r * kSeg + tid]; }
         }
-        __syncthreads();   // all reads of the weight tiles are done
 #pragma unroll
         for (int r = 0; r < kTileY; ++r) { s_wl[r * kSeg + tid] = al[r]; s_wr[r * kSeg + tid] = ar[r]; }
         __syncthreads();
@@ -288,37 +309,42 @@ __global__ void __launch_bounds__(kSeg) k_blur_blend(
             if (out_l) {  // CPU-technique depth outputs: u8 = trunc(v*255) mod 256, /255 (Q1); staged in place
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    long long il = (long long)(vl[j] * 255.0f), ir = (long long)(vr[j] * 255.0f);
-                    s_wl[pr * kSeg + c0 + j] = (float)(int)(il & 255) / 255.0f;
-                    s_wr[pr * kSeg + c0 + j] = (float)(int)(ir & 255) / 255.0f;
+                    s_wl[pr * kSeg + c0 + j] = s_q[wrap_u8(vl[j] * 255.0f)];
+                    s_wr[pr * kSeg + c0 + j] = s_q[wrap_u8(vr[j] * 255.0f)];
                 }
             }
         }
         if (out_l) {
             __syncthreads();
             const int npx = min(kSeg, w - x0);
-            for (int r = 0; r < kTileY; ++r) {
-                const int y = y0 + r;
-                if (y >= h) break;
-                float* pl = out_l + (((int64_t)frame * h + y) * w + x0) * 3;
-                float* pr_ = out_r + (((int64_t)frame * h + y) * w + x0) * 3;
-                const float* sl = s_wl + r * kSeg;
-                const float* sr = s_wr + r * kSeg;
-                if (vec_out) {
-                    const int nvec = (npx * 3) >> 2;  // npx % 4 == 0 here
-                    for (int m = tid; m < nvec; m += kSeg) {
-                        const int f0 = 4 * m;
-                        const int p0 = f0 / 3, k = f0 - 3 * p0;       // float f0 is channel k of pixel p0
-                        const int p1 = p0 + 1 < kSeg ? p0 + 1 : p0;
-                        const float a0 = sl[p0], a1 = sl[p1], c0 = sr[p0], c1 = sr[p1];
-                        // floats f0..f0+3 belong to pixel p0 for the first (3 - k) of them, then to p0 + 1
-                        float4 a = make_float4(a0, (k < 2) ? a0 : a1, (k < 1) ? a0 : a1, a1);
-                        float4 c = make_float4(c0, (k < 2) ? c0 : c1, (k < 1) ? c0 : c1, c1);
-                        st_stream_f4(reinterpret_cast<float4*>(pl) + m, a, pol);
-                        st_stream_f4(reinterpret_cast<float4*>(pr_) + m, c, pol);
+            const int rows = min(kTileY, h - y0);
+            float* pl = out_l + (((int64_t)frame * h + y0) * w + x0) * 3;
+            float* pr_ = out_r + (((int64_t)frame * h + y0) * w + x0) * 3;
+            if (vec_out) {
+                // float4 m of a row holds floats 4m..4m+3: channel k.. of pixel p0, then pixel p0 + 1 (npx % 4 == 0 here,
+                // so 3 * npx / 4 <= 192 float4 per row: one per thread)
+                const int nvec = (npx * 3) >> 2;
+                if (tid < nvec) {
+                    const int f0 = 4 * tid;
+                    const int p0 = f0 / 3, k = f0 - 3 * p0;
+                    const int p1 = p0 + 1 < kSeg ? p0 + 1 : p0;
+                    float4* ql = reinterpret_cast<float4*>(pl) + tid;
+                    float4* qr = reinterpret_cast<float4*>(pr_) + tid;
+                    const int pitch4 = (w * 3) >> 2;      // w % 4 == 0
+                    for (int r = 0; r < rows; ++r) {
+                        const float a0 = s_wl[r * kSeg + p0], a1 = s_wl[r * kSeg + p1];
+                        const float c0 = s_wr[r * kSeg + p0], c1 = s_wr[r * kSeg + p1];
+                        st_stream_f4(ql, make_float4(a0, (k < 2) ? a0 : a1, (k < 1) ? a0 : a1, a1), pol);
+                        st_stream_f4(qr, make_float4(c0, (k < 2) ? c0 : c1, (k < 1) ? c0 : c1, c1), pol);
+                        ql += pitch4; qr += pitch4;
                     }
-                } else {
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float* sl = s_wl + r * kSeg;
+                    const float* sr = s_wr + r * kSeg;
                     for (int f = tid; f < npx * 3; f += kSeg) { pl[f] = sl[f / 3]; pr_[f] = sr[f / 3]; }
+                    pl += (int64_t)w * 3; pr_ += (int64_t)w * 3;
                 }
             }
         }
@@ -413,7 +439,7 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     if (per_frame > items) per_frame = items;
     if (per_frame < 1) per_frame = 1;
     const int rw = (kSeg + bs + kRowPad + 3) & ~3;
-    size_t smem = ((size_t)2 * (kTileY + 2 * v) * kSeg + (size_t)kTileY * rw) * sizeof(float);
+    size_t smem = ((size_t)2 * kTileY * kSeg + (size_t)kTileY * rw) * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     prof_begin(K_BLUR_BLEND, s);
     launch_blend_v(v, dim3(per_frame, n), smem, s, gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, bs, radius, lut,
