@@ -238,16 +238,32 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
                 out[x] = px;
             }
         } else {  // naive_interpolating, SIG:1871-1892
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
-                int s = win[x];
-                row[x] = (s != empty) ? (img[s] & 0x00FFFFFFu) : 0u;
+            // An "anchor" is a pixel that stops the reference's right-border scan: non-black and filled.  A fill started
+            // at l writes [l, r) where r is the next anchor, and reads row[l - 1] >= the previous anchor, so everything the
+            // sequential loop does between two neighbouring anchors stays between them and anchors never change: the
+            // intervals are independent.  One thread replays the reference's loop on each interval that holds a gap.
+            uint32_t* abits = row + w;
+            for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
+                bool anc = false;
+                if (x < w) {
+                    const int s = win[x];
+                    const uint32_t v = (s != empty) ? (img[s] & 0x00FFFFFFu) : 0u;
+                    row[x] = v;
+                    anc = (s != empty) && px_sum(v) != 0;
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, anc);
+                if ((threadIdx.x & 31) == 0) abits[x >> 5] = b;
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                // only unfilled pixels can start a gap: walk the zero bits of the filled map instead of every column
-                for (int wi = 0; wi < nwords; ++wi) {
+            for (int x = (int)threadIdx.x - 1; x < w; x += blockDim.x) {    // x = -1: the interval left of the first anchor
+                if (x >= 0 && !((abits[x >> 5] >> (x & 31)) & 1u)) continue;
+                const int dn = bit_dist_right(abits, nwords, x, 1 << 29);
+                const int nx = (dn < (1 << 29)) ? x + dn : w;               // next anchor, or the end of the row
+                // only unfilled pixels can start a gap: walk the zero bits of the filled map inside (x, nx)
+                for (int wi = (x + 1) >> 5; wi <= ((nx - 1) >> 5) && x + 1 < nx; ++wi) {
                   uint32_t um = ~bits[wi];
-                  if (((wi + 1) << 5) > w) um &= (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+                  if ((wi << 5) < x + 1) um &= 0xffffffffu << ((x + 1) & 31);
+                  if (((wi + 1) << 5) > nx) um &= (nx & 31) ? ((1u << (nx & 31)) - 1u) : 0xffffffffu;
                   while (um) {
                     const int l = (wi << 5) + __ffs(um) - 1;
                     um &= um - 1;
@@ -261,18 +277,18 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
                     if (px_sum(lb) == 0) lb = rb;
                     else if (px_sum(rb) == 0) rb = lb;
                     const int total = 1 + r - l;
-                    double stepv[3];
+                    float stepv[3];   // float32 array / int64 scalar stays float32 in numba
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
                         float df = (float)((rb >> (8 * ch)) & 255u) - (float)((lb >> (8 * ch)) & 255u);
-                        stepv[ch] = (double)df / (double)total;
+                        stepv[ch] = df / (float)total;
                     }
                     for (int c = l; c < r; ++c) {
                         uint32_t px = 0;
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
-                            double prod = stepv[ch] * (double)(c - l + 1);
-                            uint32_t inc = (uint32_t)(long long)prod & 255u;   // float -> uint8 wraps (Q5)
+                            float prod = stepv[ch] * (float)(c - l + 1);
+                            uint32_t inc = (uint32_t)__float2int_rz(prod) & 255u;   // float -> uint8 wraps (Q5)
                             uint32_t v = (((lb >> (8 * ch)) & 255u) + inc) & 255u;
                             px |= v << (8 * ch);
                         }
@@ -304,7 +320,7 @@ cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
             k_warp_rows<CS_FILL_NAIVE><<<grid, 256, smem, s>>>(a);
             break;
         case CS_FILL_NAIVE_INTERP:
-            smem = simg + (size_t)a.w * 8 + nwords * 4;
+            smem = simg + (size_t)a.w * 8 + nwords * 8;
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_warp_rows<CS_FILL_NAIVE_INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k_warp_rows<CS_FILL_NAIVE_INTERP><<<grid, 256, smem, s>>>(a);

@@ -77,3 +77,18 @@ def index_probe_image(h, w):
 def probe_to_float(img_u8):
     """float image whose truncating quantisation (Q2) gives back img_u8 exactly."""
     return ((img_u8.astype(np.float32) + np.float32(0.5)) / np.float32(255.0)).astype(np.float32)
+
+
+def dark_case(seed, h=24, w=333):
+    """Dark image + noisy depth (0..255) that exercise the interpolating fill's rare paths: ramps between black or
+    near-black borders, black ramp values that start new gaps, black-but-filled pixels (SIG:1871-1892)."""
+    rng = np.random.default_rng(50 + seed)
+    img = rng.integers(0, 3, (h, w, 3), dtype=np.uint8) * rng.integers(0, 2, (h, w, 1), dtype=np.uint8)
+    img[:, ::7] = rng.integers(0, 256, (h, (w + 6) // 7, 3), dtype=np.uint8)
+    if seed % 3 == 2:
+        img[:] = 0
+        img[:, 100:110] = 9
+    d = (rng.random((h, w), dtype=np.float32) * np.float32(255)).astype(np.float32)
+    if seed % 3:
+        d[:, 150:200] = np.float32(200)
+    return img, d

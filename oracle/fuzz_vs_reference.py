@@ -1,0 +1,110 @@
+"""Fuzz the oracle against the UNMODIFIED reference (needs /root/reference; build container only).
+
+TEST INFRASTRUCTURE ONLY.  The committed fixtures pin the oracle on a fixed set of inputs; this script hunts for
+rare disagreements (rounding cases, dark images, extreme parameters) on random ones:
+
+    python oracle/fuzz_vs_reference.py [iterations] [seed]
+
+Every disagreement is printed with the parameters that reproduce it; anything found becomes a fixture
+(oracle/make_golden.py) after the oracle is fixed.
+"""
+import sys
+import os
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+import oracle  # noqa: E402
+
+FILLS = ['none', 'naive', 'naive_interpolating', 'polylines_soft', 'polylines_sharp', 'inverse', 'hybrid_edge',
+         'none_post', 'inverse_post', 'hybrid_edge_plus']
+
+
+def random_case(rng):
+    h = int(rng.integers(1, 20))
+    w = int(rng.integers(2, 200))
+    style = int(rng.integers(0, 5))
+    if style == 0:      # uniform noise
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    elif style == 1:    # dark: ramps between near-black borders, black pixels that are really there
+        img = rng.integers(0, 3, (h, w, 3), dtype=np.uint8) * rng.integers(0, 2, (h, w, 1), dtype=np.uint8)
+        img[:, ::7] = rng.integers(0, 256, (h, (w + 6) // 7, 3), dtype=np.uint8)
+    elif style == 2:    # mostly black
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, w // 3: w // 3 + 4] = rng.integers(0, 256, 3, dtype=np.uint8)
+    elif style == 3:    # bright (uint8 sums wrap)
+        img = rng.integers(250, 256, (h, w, 3), dtype=np.uint8)
+    else:               # smooth gradient
+        img = np.broadcast_to((np.arange(w) * 255 // max(w - 1, 1)).astype(np.uint8)[None, :, None], (h, w, 3)).copy()
+    dstyle = int(rng.integers(0, 5))
+    if dstyle == 0:
+        d = rng.random((h, w), dtype=np.float32) * np.float32(255)
+    elif dstyle == 1:
+        d = np.broadcast_to(np.linspace(0, 255, w, dtype=np.float32)[None], (h, w)).copy()
+    elif dstyle == 2:
+        d = np.full((h, w), 128, np.float32)
+        d[:, w // 4: w // 2] = 250
+    elif dstyle == 3:
+        d = np.round(rng.random((h, w), dtype=np.float32) * 4) * np.float32(60)
+    else:
+        d = np.full((h, w), 77, np.float32)   # flat
+    div = float(rng.choice([0.5, 2.0, 3.5, 6.0, 10.0, 15.0])) * float(rng.choice([-1, 1]))
+    sep = float(rng.choice([0.0, 0.0, 1.0, -2.5]))
+    expo = float(rng.choice([1.0, 2.0, 0.7]))
+    conv = float(rng.choice([0.0, 0.5, 1.0, 0.3]))
+    return img, d.astype(np.float32), div, sep, expo, conv
+
+
+def main():
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    assert ref_loader.reference_available(), "needs /root/reference"
+    Node = ref_loader.load_node_class()
+    sig = sys.modules[Node.__module__].sig
+    rng = np.random.default_rng(seed)
+    bad = {}
+    for it in range(iters):
+        img, d, div, sep, expo, conv = random_case(rng)
+        for fill in FILLS:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = np.asarray(sig.apply_stereo_divergence(img.copy(), d.copy(), div, sep, expo, fill, conv))
+            got = oracle.apply_stereo_divergence(img, d, div, sep, expo, fill, conv)
+            diff = np.abs(ref.astype(np.int32) - got.astype(np.int32))
+            if diff.max() > 0:
+                bad[fill] = bad.get(fill, 0) + 1
+                print(f"MISMATCH it={it} seed={seed} fill={fill} shape={img.shape[:2]} div={div} sep={sep} expo={expo} "
+                      f"conv={conv}: {int((diff > 0).sum())} values, max {int(diff.max())}")
+    print("iterations", iters, "mismatching cases per fill:", bad if bad else "none")
+    # forward_warp_gpu (SIG:277-450) on torch-CPU: mask bit-exact, image to float32 rounding
+    import torch
+    gbad = 0
+    for it in range(max(1, iters // 4)):
+        img, d, div, sep, expo, conv = random_case(rng)
+        h, w = d.shape
+        imgf = (img.astype(np.float32) / np.float32(255)).transpose(2, 0, 1).copy()
+        d01 = (d / np.float32(255)).astype(np.float32)
+        div_px, sep_px = div / 100.0 * w, sep / 100.0 * w
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rw, rm = sig.forward_warp_gpu(torch.from_numpy(imgf)[None], torch.from_numpy(d01)[None], div_px, sep_px,
+                                          expo, conv)
+        ow, om = oracle.gpuwarp_eye(imgf, d01, div_px, sep_px, expo, conv)
+        mm = int((rm[0].numpy().astype(bool) != om.astype(bool)).sum())
+        err = float(np.abs(rw[0].numpy() - ow).max())
+        tol = 2e-5 if expo in (1.0, 2.0) else 1e-4
+        if mm or err > tol:
+            gbad += 1
+            print(f"GPUWARP MISMATCH it={it} seed={seed} shape={(h, w)} div_px={div_px} sep_px={sep_px} expo={expo} "
+                  f"conv={conv}: mask {mm}, image err {err:.3g}")
+    print("forward_warp_gpu cases", max(1, iters // 4), "mismatching:", gbad)
+    return 1 if (bad or gbad) else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

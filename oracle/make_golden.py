@@ -311,6 +311,34 @@ def node_record(spec, img, dep, outs, blur):
     return rec
 
 
+DARK_CASES = [dict(name=f"{i:03d}", seed=sd, div=dv, sep=sp, fill=fl)
+              for i, (sd, dv, sp, fl) in enumerate(
+                  [(s_, d_, p_, 'naive_interpolating') for s_ in (0, 1, 2, 3, 4) for d_, p_ in ((6.0, 0.0), (-6.0, 1.0), (15.0, -2.0))]
+                  + [(1, 6.0, 0.0, f_) for f_ in ('naive', 'polylines_soft', 'polylines_sharp', 'none_post', 'hybrid_edge_plus')])]
+
+
+def main_dark():
+    """python oracle/make_golden.py dark -- apply_stereo_divergence on dark images (found by oracle/fuzz_vs_reference.py:
+    the interpolating fill's ramp arithmetic is float32, which only shows on a fraction of a percent of ramp values)."""
+    assert ref_loader.reference_available(), "needs /root/reference"
+    Node = ref_loader.load_node_class()
+    sig = sys.modules[Node.__module__].sig
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    manifest["dark"] = []
+    for spec in DARK_CASES:
+        img, d = syn.dark_case(spec["seed"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = np.asarray(sig.apply_stereo_divergence(img.copy(), d.copy(), spec["div"], spec["sep"], 1.0, spec["fill"], 0.5))
+        np.savez_compressed(os.path.join(GOLDEN, f"dark_{spec['name']}.npz"), crc=crc(img, d), out=out.astype(np.uint8))
+        manifest["dark"].append(spec)
+        print("dark", spec["name"], spec["fill"], flush=True)
+    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+    print("dark cases:", len(DARK_CASES))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -348,5 +376,7 @@ if __name__ == "__main__":
         main_post()
     elif len(sys.argv) > 1 and sys.argv[1] == "resize":
         main_resize()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dark":
+        main_dark()
     else:
         main()

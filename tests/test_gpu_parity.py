@@ -121,6 +121,22 @@ def test_compose_modes(gu, oracle):
         assert np.array_equal(mk, (ref.astype(np.int32).sum(-1) == 0).astype(np.float32))
 
 
+@pytest.mark.parametrize("spec", MAN["dark"], ids=[s["name"] + "_" + s["fill"] for s in MAN["dark"]])
+def test_dark_images_vs_reference(gu, oracle, spec):
+    """The interpolating fill's chains: ramps between black / near-black borders produce black pixels that start new
+    gaps reading already-interpolated neighbours, and black-but-filled pixels turn into scan stoppers once overwritten
+    (SIG:1871-1892); its ramp arithmetic is float32.  The kernel replays each anchor-to-anchor interval independently.
+    Bit-exact against the reference's fixture (and the oracle); Hybrid colours within 1 LSB."""
+    g = load_golden("dark", spec["name"])
+    img, d = syn.dark_case(spec["seed"])
+    got = gu.warp_fill(img, d, spec["fill"], spec["div"], spec["sep"], 1.0, 0.5)[..., :3]
+    if spec["fill"].startswith("hybrid"):
+        assert np.abs(got.astype(np.int32) - g["out"].astype(np.int32)).max() <= 1
+    else:
+        assert np.array_equal(got, g["out"]), (got != g["out"]).sum()
+        assert np.array_equal(got, oracle.apply_stereo_divergence(img, d, spec["div"], spec["sep"], 1.0, spec["fill"], 0.5))
+
+
 # ------------------------------------------------------------------------------------------ N1 resize
 @pytest.mark.parametrize("spec", MAN["resize"], ids=[s["name"] for s in MAN["resize"]])
 def test_depth_resize_vs_reference(gu, oracle, spec):

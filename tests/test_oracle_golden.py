@@ -61,6 +61,17 @@ def test_stage_vs_reference(oracle, spec):
         assert np.abs(warped - g["warped"]).max() <= 2e-5
 
 
+@pytest.mark.parametrize("spec", MAN["dark"], ids=[s["name"] + "_" + s["fill"] for s in MAN["dark"]])
+def test_dark_images_vs_reference(oracle, spec):
+    """apply_stereo_divergence on dark images (black ramp values, black-but-filled pixels; the interpolating fill's
+    float32 ramp arithmetic): bit-exact against the reference."""
+    g = load_golden("dark", spec["name"])
+    img, d = syn.dark_case(spec["seed"])
+    assert _crc(img, d) == int(g["crc"])
+    out = oracle.apply_stereo_divergence(img, d, spec["div"], spec["sep"], 1.0, spec["fill"], 0.5)
+    assert np.array_equal(out, g["out"])
+
+
 @pytest.mark.parametrize("spec", MAN["resize"], ids=[s["name"] for s in MAN["resize"]])
 def test_resize_vs_reference(oracle, spec):
     """N1 depth resize (GS:141-148 / GS:214-220): bit-exact against torch's strict (ATEN_CPU_CAPABILITY=default)
