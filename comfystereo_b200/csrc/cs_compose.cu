@@ -102,4 +102,38 @@ cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, i
     return cudaGetLastError();
 }
 
+// Host transport (cs_host.cu): the depth outputs are three identical channels and the mask is 0/1, so only one
+// channel of each depth output and one byte per mask pixel cross PCIe; the host side re-expands them.
+__global__ void __launch_bounds__(256) k_compact_outputs(const float* __restrict__ dl3, const float* __restrict__ dr3,
+                                                         const float* __restrict__ mask, int64_t npx, int64_t nmask,
+                                                         float* __restrict__ cdl, float* __restrict__ cdr,
+                                                         uint8_t* __restrict__ cmask) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < npx; i += stride) { cdl[i] = dl3[3 * i]; cdr[i] = dr3[3 * i]; }
+    // 4 mask pixels per thread (nmask4 words), tail by the first threads
+    const int64_t n4 = nmask >> 2;
+    const bool al = ((uintptr_t)mask % 16 == 0) && ((uintptr_t)cmask % 4 == 0);
+    if (al) {
+        for (int64_t i = t0; i < n4; i += stride) {
+            const float4 m = reinterpret_cast<const float4*>(mask)[i];
+            const uint32_t b = (m.x != 0.0f ? 1u : 0u) | (m.y != 0.0f ? 1u << 8 : 0u) | (m.z != 0.0f ? 1u << 16 : 0u) |
+                               (m.w != 0.0f ? 1u << 24 : 0u);
+            reinterpret_cast<uint32_t*>(cmask)[i] = b;
+        }
+        for (int64_t i = (n4 << 2) + t0; i < nmask; i += stride) cmask[i] = mask[i] != 0.0f ? 1 : 0;
+    } else {
+        for (int64_t i = t0; i < nmask; i += stride) cmask[i] = mask[i] != 0.0f ? 1 : 0;
+    }
+}
+
+cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,
+                                   float* cdl, float* cdr, uint8_t* cmask, cudaStream_t s) {
+    prof_begin(K_MISC, s);
+    k_compact_outputs<<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
+    prof_end(K_MISC, s);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace cs

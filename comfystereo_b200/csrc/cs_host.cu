@@ -1,17 +1,25 @@
 // cs_host.cu -- cs_stereo_batch_host: the hot path with HOST buffers, the shape in which ComfyUI
 // hands IMAGE tensors to the node and expects them back (GS:126, GS:161-171, GS:298-307).
 //
-// Frames stream through two device slots: while chunk i runs its kernels on the compute stream,
+// Frames stream through kSlots device slots: while chunk i runs its kernels on the compute stream,
 // chunk i+1 is uploading on the copy-in stream and chunk i-1 is downloading on the copy-out stream.
 //
 // Page-locked caller buffers are copied directly (cudaMemcpyAsync is truly asynchronous on them).
 // Pageable buffers -- what ComfyUI passes in, and what a large result tensor has to be -- are not
 // handed to the driver (measured on B200: 2.2 GB/s into fresh pageable memory): the library owns
-// two page-locked bounce buffers per direction and moves data between them and the caller's memory
+// page-locked bounce buffers (one per slot and direction) and moves data between them and the caller's memory
 // with a team of host threads, overlapped with the GPU work of the neighbouring chunks.
+// The depth outputs are three identical channels and the mask is 0/1: when the host has threads to spare, only
+// one channel of each depth output and one byte per mask pixel cross PCIe (a small kernel compacts them) and the
+// thread team expands them into the caller's tensors while the next chunk is in flight -- 70 MB instead of 116 MB
+// per 1080p side-by-side frame on the bus that bounds this call.
 // Device buffers, bounce buffers and streams are cached per device; cs_host_release() frees them.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -19,19 +27,27 @@
 
 #include "cs_internal.cuh"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 namespace cs {
+
+constexpr int kSlots = 4;   // chunks in flight: upload, kernels, download and the host-side drain each hold one
 
 struct HostCtx {
     int device = -1;
     size_t in_bytes = 0, out_bytes = 0, ws_bytes = 0;
-    size_t bounce_in_bytes = 0, bounce_out_bytes = 0;
-    char* d_in[2] = {nullptr, nullptr};
-    char* d_out[2] = {nullptr, nullptr};
-    char* h_in[2] = {nullptr, nullptr};     // page-locked bounce buffers (only when the caller's memory is pageable)
-    char* h_out[2] = {nullptr, nullptr};
+    size_t bounce_in_bytes = 0, bounce_out_bytes = 0, cmp_bytes = 0;
+    char* d_cmp[kSlots] = {};    // compact depth / mask outputs (device) ...
+    char* h_cmp[kSlots] = {};    // ... and their page-locked landing buffers
+    char* d_in[kSlots] = {};
+    char* d_out[kSlots] = {};
+    char* h_in[kSlots] = {};     // page-locked bounce buffers (only when the caller's memory is pageable)
+    char* h_out[kSlots] = {};
     char* d_ws = nullptr;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
     bool ready = false;
 };
 
@@ -41,11 +57,13 @@ static HostCtx g_ctx[16];
 static void ctx_free(HostCtx& c) {
     if (!c.ready) return;
     cudaSetDevice(c.device);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (c.d_in[i]) cudaFree(c.d_in[i]);
         if (c.d_out[i]) cudaFree(c.d_out[i]);
         if (c.h_in[i]) cudaFreeHost(c.h_in[i]);
         if (c.h_out[i]) cudaFreeHost(c.h_out[i]);
+        if (c.d_cmp[i]) cudaFree(c.d_cmp[i]);
+        if (c.h_cmp[i]) cudaFreeHost(c.h_cmp[i]);
         if (c.ev_in[i]) cudaEventDestroy(c.ev_in[i]);
         if (c.ev_run[i]) cudaEventDestroy(c.ev_run[i]);
         if (c.ev_out[i]) cudaEventDestroy(c.ev_out[i]);
@@ -58,22 +76,28 @@ static void ctx_free(HostCtx& c) {
 }
 
 static cudaError_t ctx_ensure(HostCtx& c, int device, size_t in_bytes, size_t out_bytes, size_t ws_bytes,
-                              bool bounce_in, bool bounce_out) {
+                              size_t cmp_bytes, bool bounce_in, bool bounce_out) {
     cudaError_t e;
     const bool fits = c.ready && c.in_bytes >= in_bytes && c.out_bytes >= out_bytes && c.ws_bytes >= ws_bytes &&
+                      c.cmp_bytes >= cmp_bytes &&
                       (!bounce_in || c.bounce_in_bytes >= in_bytes) && (!bounce_out || c.bounce_out_bytes >= out_bytes);
     if (fits) return cudaSuccess;
     const bool keep_in = c.ready && c.bounce_in_bytes > 0, keep_out = c.ready && c.bounce_out_bytes > 0;
+    if (c.ready && c.cmp_bytes > cmp_bytes) cmp_bytes = c.cmp_bytes;
     ctx_free(c);
     c.device = device;
     c.ready = true;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if ((e = cudaMalloc((void**)&c.d_in[i], in_bytes)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void**)&c.d_out[i], out_bytes)) != cudaSuccess) return e;
         if (bounce_in || keep_in)
             if ((e = cudaHostAlloc((void**)&c.h_in[i], in_bytes, cudaHostAllocDefault)) != cudaSuccess) return e;
         if (bounce_out || keep_out)
             if ((e = cudaHostAlloc((void**)&c.h_out[i], out_bytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+        if (cmp_bytes) {
+            if ((e = cudaMalloc((void**)&c.d_cmp[i], cmp_bytes)) != cudaSuccess) return e;
+            if ((e = cudaHostAlloc((void**)&c.h_cmp[i], cmp_bytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+        }
         if ((e = cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&c.ev_run[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -82,7 +106,7 @@ static cudaError_t ctx_ensure(HostCtx& c, int device, size_t in_bytes, size_t ou
     if ((e = cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&c.s_run, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    c.in_bytes = in_bytes; c.out_bytes = out_bytes; c.ws_bytes = ws_bytes;
+    c.in_bytes = in_bytes; c.out_bytes = out_bytes; c.ws_bytes = ws_bytes; c.cmp_bytes = cmp_bytes;
     c.bounce_in_bytes = (bounce_in || keep_in) ? in_bytes : 0;
     c.bounce_out_bytes = (bounce_out || keep_out) ? out_bytes : 0;
     return cudaSuccess;
@@ -98,11 +122,23 @@ struct Span { char* dst; const char* src; size_t bytes; };
 
 // memcpy a list of spans with a team of threads (first touch of fresh pageable pages is the expensive part;
 // it parallelises well)
-static void parallel_copy(const std::vector<Span>& spans) {
+static std::atomic<int> g_active{0};   // cs_stereo_batch_host calls in flight in this process
+
+// Host threads this call may use: the machine's threads shared between the ranks of a one-process-per-GPU job
+// (LOCAL_WORLD_SIZE, set by torchrun) or the pipelines this process is running side by side.
+static int host_share() {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (!hw) hw = 8;
+    int peers = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) peers = std::max(1, atoi(e));
+    peers = std::max(peers, g_active.load());
+    return std::max(1, (int)hw / peers);
+}
+
+static void parallel_copy(const std::vector<Span>& spans, int team) {
     size_t total = 0;
     for (const auto& s : spans) total += s.bytes;
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<size_t>(std::max(1u, std::min(hw ? hw : 8u, 16u)), total / (4u << 20) + 1);
+    int nt = (int)std::min<size_t>((size_t)std::max(1, std::min(team, 16)), total / (4u << 20) + 1);
     if (nt <= 1) {
         for (const auto& s : spans) memcpy(s.dst, s.src, s.bytes);
         return;
@@ -116,6 +152,65 @@ static void parallel_copy(const std::vector<Span>& spans) {
             pos += s.bytes;
             if (pos >= hi) break;
         }
+    };
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+}
+
+// depth: one channel -> three identical ones; mask: bytes -> floats (the inverse of k_compact_outputs).
+// The destination is written once and not read back here: non-temporal stores skip the read-for-ownership of every
+// cache line, which is what bounds this loop while the DMA engines use the same memory.
+static void expand3(const float* src, float* dst, size_t p0, size_t p1) {
+    size_t i = p0;
+#if defined(__SSE2__)
+    for (; i < p1 && ((uintptr_t)(dst + 3 * i) & 15); ++i) { const float v = src[i]; dst[3 * i] = v; dst[3 * i + 1] = v; dst[3 * i + 2] = v; }
+    for (; i + 4 <= p1; i += 4) {
+        const __m128 v = _mm_loadu_ps(src + i);                       // a b c d
+        float* d = dst + 3 * i;
+        _mm_stream_ps(d, _mm_shuffle_ps(v, v, _MM_SHUFFLE(1, 0, 0, 0)));      // a a a b
+        _mm_stream_ps(d + 4, _mm_shuffle_ps(v, v, _MM_SHUFFLE(2, 2, 1, 1)));  // b b c c
+        _mm_stream_ps(d + 8, _mm_shuffle_ps(v, v, _MM_SHUFFLE(3, 3, 3, 2)));  // c d d d
+    }
+#endif
+    for (; i < p1; ++i) { const float v = src[i]; dst[3 * i] = v; dst[3 * i + 1] = v; dst[3 * i + 2] = v; }
+}
+
+static void expand_mask(const uint8_t* src, float* dst, size_t m0, size_t m1) {
+    size_t i = m0;
+#if defined(__SSE2__)
+    for (; i < m1 && ((uintptr_t)(dst + i) & 15); ++i) dst[i] = (float)src[i];
+    const __m128i zero = _mm_setzero_si128();
+    for (; i + 16 <= m1; i += 16) {
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i lo = _mm_unpacklo_epi8(b, zero), hi = _mm_unpackhi_epi8(b, zero);
+        _mm_stream_ps(dst + i, _mm_cvtepi32_ps(_mm_unpacklo_epi16(lo, zero)));
+        _mm_stream_ps(dst + i + 4, _mm_cvtepi32_ps(_mm_unpackhi_epi16(lo, zero)));
+        _mm_stream_ps(dst + i + 8, _mm_cvtepi32_ps(_mm_unpacklo_epi16(hi, zero)));
+        _mm_stream_ps(dst + i + 12, _mm_cvtepi32_ps(_mm_unpackhi_epi16(hi, zero)));
+    }
+#endif
+    for (; i < m1; ++i) dst[i] = (float)src[i];
+}
+
+static void expand_slice(const float* cdl, const float* cdr, const uint8_t* cm, float* dl, float* dr, float* mask,
+                         size_t p0, size_t p1, size_t m0, size_t m1) {
+    expand3(cdl, dl, p0, p1);
+    expand3(cdr, dr, p0, p1);
+    expand_mask(cm, mask, m0, m1);
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
+
+static void parallel_expand(const float* cdl, const float* cdr, const uint8_t* cm, float* dl, float* dr, float* mask,
+                            size_t npx, size_t nmask, int team) {
+    int nt = (int)std::min<size_t>((size_t)std::max(1, std::min(team, 16)), (npx * 24 + nmask * 4) / (4u << 20) + 1);
+    if (nt <= 1) { expand_slice(cdl, cdr, cm, dl, dr, mask, 0, npx, 0, nmask); return; }
+    auto work = [&](int t) {
+        expand_slice(cdl, cdr, cm, dl, dr, mask, npx * t / nt, npx * (t + 1) / nt, nmask * t / nt, nmask * (t + 1) / nt);
     };
     std::vector<std::thread> th;
     th.reserve(nt - 1);
@@ -165,12 +260,23 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     if (chunk < group) chunk = group;
     if (chunk > n) chunk = n;
     const size_t ws_bytes = cs_workspace_bytes(p, chunk, h, w);
+    struct Active { Active() { g_active.fetch_add(1); } ~Active() { g_active.fetch_sub(1); } } active;
+    const int team = host_share();
+    // compact transport of the depth outputs and the mask when the host has the threads to expand them
+    bool compact = team >= 8;
+    if (const char* e = getenv("COMFYSTEREO_COMPACT_D2H")) compact = atoi(e) != 0;
     const bool bounce_in = !(is_pinned(image) && is_pinned(depth));
-    const bool bounce_out = !(is_pinned(stereo) && is_pinned(depth_l) && is_pinned(depth_r) && is_pinned(mask));
+    const bool stereo_pinned = is_pinned(stereo);
+    const bool bounce_out = compact ? !stereo_pinned
+                                    : !(stereo_pinned && is_pinned(depth_l) && is_pinned(depth_r) && is_pinned(mask));
+    auto al256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t cmp_depth = al256((size_t)chunk * px * 4), cmp_mask = al256((size_t)chunk * hm * wm);
+    const size_t cmp_bytes = compact ? 2 * cmp_depth + cmp_mask : 0;
 
     std::lock_guard<std::mutex> lk(g_mu[device]);
     HostCtx& cx = g_ctx[device];
-    cudaError_t e = ctx_ensure(cx, device, (size_t)chunk * in_frame, (size_t)chunk * out_frame, ws_bytes, bounce_in, bounce_out);
+    cudaError_t e = ctx_ensure(cx, device, (size_t)chunk * in_frame, (size_t)chunk * out_frame, ws_bytes, cmp_bytes,
+                               bounce_in, bounce_out);
     if (e != cudaSuccess) { ctx_free(cx); HOST_FAIL(CS_ERR_CUDA, "device buffers: %s", cudaGetErrorString(e)); }
 
     // spans of chunk `it` between the caller's tensors and a contiguous slot
@@ -184,6 +290,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     auto out_spans = [&](int f0, int m, const char* slot) {
         std::vector<Span> v;
         v.push_back({(char*)(stereo + (size_t)f0 * ho * wo * 3), slot, (size_t)m * b_st});
+        if (compact) return v;    // depth outputs and mask come through the compact buffers
         v.push_back({(char*)(depth_l + (size_t)f0 * px * 3), slot + (size_t)m * b_st, (size_t)m * b_d});
         v.push_back({(char*)(depth_r + (size_t)f0 * px * 3), slot + (size_t)m * (b_st + b_d), (size_t)m * b_d});
         v.push_back({(char*)(mask + (size_t)f0 * hm * wm), slot + (size_t)m * (b_st + 2 * b_d), (size_t)m * b_m});
@@ -191,10 +298,58 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     };
 
     const int nchunks = (n + chunk - 1) / chunk;
-    // iteration `it` enqueues chunk `it` and, meanwhile on the host, drains the results of chunk `it - 1`
-    for (int it = 0; it <= nchunks; ++it) {
-        if (it < nchunks) {
-            const int f0 = it * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = it & 1;
+    // Producer (this thread) enqueues chunk after chunk; when results need host work (bounce copy and / or expansion)
+    // a consumer thread drains them in order, so that the uploads and kernels of later chunks are never held up by it.
+    const bool drain = bounce_out || compact;
+    std::mutex mu;
+    std::condition_variable cv;
+    int enqueued = 0, drained = 0;      // chunks whose download has been enqueued / whose results reached the caller
+    bool stop = false;
+    int drain_rc = CS_OK;
+    double t_event = 0.0, t_host = 0.0, t_slot = 0.0;   // COMFYSTEREO_HOST_TRACE=1: where the consumer / producer waited
+    const auto call0 = std::chrono::steady_clock::now();
+    auto consumer = [&]() {
+        cudaSetDevice(device);
+        for (int pit = 0; pit < nchunks; ++pit) {
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return enqueued > pit || stop; });
+                if (enqueued <= pit) return;
+            }
+            const int f0 = pit * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = pit % kSlots;
+            const auto c0 = std::chrono::steady_clock::now();
+            if (cudaEventSynchronize(cx.ev_out[sl]) != cudaSuccess) drain_rc = CS_ERR_CUDA;
+            const auto c1 = std::chrono::steady_clock::now();
+            if (bounce_out) parallel_copy(out_spans(f0, m, cx.h_out[sl]), team);
+            if (compact)
+                parallel_expand((const float*)cx.h_cmp[sl], (const float*)(cx.h_cmp[sl] + cmp_depth),
+                                (const uint8_t*)(cx.h_cmp[sl] + 2 * cmp_depth), depth_l + (size_t)f0 * px * 3,
+                                depth_r + (size_t)f0 * px * 3, mask + (size_t)f0 * hm * wm, (size_t)m * px,
+                                (size_t)m * hm * wm, team);
+            const auto c2 = std::chrono::steady_clock::now();
+            t_event += std::chrono::duration<double>(c1 - c0).count();
+            t_host += std::chrono::duration<double>(c2 - c1).count();
+            { std::lock_guard<std::mutex> g(mu); drained = pit + 1; }
+            cv.notify_all();
+        }
+    };
+    std::thread drainer;
+    if (drain) drainer = std::thread(consumer);
+    // every exit path stops and joins the consumer
+    struct Joiner {
+        std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& stop;
+        ~Joiner() { if (t.joinable()) { { std::lock_guard<std::mutex> g(mu); stop = true; } cv.notify_all(); t.join(); } }
+    } joiner{drainer, mu, cv, stop};
+
+    for (int it = 0; it < nchunks; ++it) {
+        {
+            const int f0 = it * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = it % kSlots;
+            if (drain && it >= kSlots) {   // the slot's host landing buffers must have been drained (chunk it - kSlots)
+                const auto w0 = std::chrono::steady_clock::now();
+                std::unique_lock<std::mutex> g(mu);
+                cv.wait(g, [&] { return drained >= it - kSlots + 1; });
+                t_slot += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+            }
             char* din = cx.d_in[sl];
             char* dout = cx.d_out[sl];
             float* d_img = (float*)din;
@@ -203,27 +358,41 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             float* d_dl = (float*)(dout + (size_t)m * b_st);
             float* d_dr = (float*)(dout + (size_t)m * (b_st + b_d));
             float* d_mk = (float*)(dout + (size_t)m * (b_st + 2 * b_d));
-            // upload: the slot's device inputs are free once the kernels of chunk it-2 are done; its bounce buffer
-            // once the upload of chunk it-2 is done
-            if (it >= 2) HOST_CUDA(cudaStreamWaitEvent(cx.s_in, cx.ev_run[sl], 0));
+            // upload: the slot's device inputs are free once the kernels of chunk it - kSlots are done; its bounce buffer
+            // once the upload of chunk it - kSlots is done
+            if (it >= kSlots) HOST_CUDA(cudaStreamWaitEvent(cx.s_in, cx.ev_run[sl], 0));
             if (bounce_in) {
-                if (it >= 2) HOST_CUDA(cudaEventSynchronize(cx.ev_in[sl]));
-                parallel_copy(in_spans(f0, m, cx.h_in[sl], true));
+                if (it >= kSlots) HOST_CUDA(cudaEventSynchronize(cx.ev_in[sl]));
+                parallel_copy(in_spans(f0, m, cx.h_in[sl], true), team);
                 HOST_CUDA(cudaMemcpyAsync(din, cx.h_in[sl], (size_t)m * in_frame, cudaMemcpyHostToDevice, cx.s_in));
             } else {
                 HOST_CUDA(cudaMemcpyAsync(d_img, image + (size_t)f0 * px * 3, (size_t)m * b_img, cudaMemcpyHostToDevice, cx.s_in));
                 HOST_CUDA(cudaMemcpyAsync(d_dep, depth + (size_t)f0 * dpx * c, (size_t)m * b_dep, cudaMemcpyHostToDevice, cx.s_in));
             }
             HOST_CUDA(cudaEventRecord(cx.ev_in[sl], cx.s_in));
-            // kernels: need the upload, and the slot's device outputs must have left (chunk it-2)
+            // kernels: need the upload, and the slot's device outputs must have left (chunk it - kSlots)
             HOST_CUDA(cudaStreamWaitEvent(cx.s_run, cx.ev_in[sl], 0));
-            if (it >= 2) HOST_CUDA(cudaStreamWaitEvent(cx.s_run, cx.ev_out[sl], 0));
+            if (it >= kSlots) HOST_CUDA(cudaStreamWaitEvent(cx.s_run, cx.ev_out[sl], 0));
             rc = cs_stereo_batch(p, d_img, d_dep, m, h, w, c, d_st, d_dl, d_dr, d_mk, cx.d_ws, cx.ws_bytes, cx.s_run);
             if (rc) { cudaDeviceSynchronize(); return rc; }
+            if (compact) {
+                e = launch_compact_outputs(d_dl, d_dr, d_mk, (int64_t)m * px, (int64_t)m * hm * wm,
+                                           (float*)cx.d_cmp[sl], (float*)(cx.d_cmp[sl] + cmp_depth),
+                                           (uint8_t*)(cx.d_cmp[sl] + 2 * cmp_depth), cx.s_run);
+                if (e != cudaSuccess) { cudaDeviceSynchronize(); HOST_FAIL(CS_ERR_CUDA, "compact: %s", cudaGetErrorString(e)); }
+            }
             HOST_CUDA(cudaEventRecord(cx.ev_run[sl], cx.s_run));
-            // download (the bounce buffer of this slot was drained by the host one iteration ago)
+            // download (the bounce buffers of this slot were drained by the host one iteration ago)
             HOST_CUDA(cudaStreamWaitEvent(cx.s_out, cx.ev_run[sl], 0));
-            if (bounce_out) {
+            if (compact) {
+                float* dst = stereo_pinned ? stereo + (size_t)f0 * ho * wo * 3 : (float*)cx.h_out[sl];
+                HOST_CUDA(cudaMemcpyAsync(dst, d_st, (size_t)m * b_st, cudaMemcpyDeviceToHost, cx.s_out));
+                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl], cx.d_cmp[sl], (size_t)m * px * 4, cudaMemcpyDeviceToHost, cx.s_out));
+                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl] + cmp_depth, cx.d_cmp[sl] + cmp_depth, (size_t)m * px * 4,
+                                          cudaMemcpyDeviceToHost, cx.s_out));
+                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl] + 2 * cmp_depth, cx.d_cmp[sl] + 2 * cmp_depth, (size_t)m * hm * wm,
+                                          cudaMemcpyDeviceToHost, cx.s_out));
+            } else if (bounce_out) {
                 HOST_CUDA(cudaMemcpyAsync(cx.h_out[sl], dout, (size_t)m * out_frame, cudaMemcpyDeviceToHost, cx.s_out));
             } else {
                 HOST_CUDA(cudaMemcpyAsync(stereo + (size_t)f0 * ho * wo * 3, d_st, (size_t)m * b_st, cudaMemcpyDeviceToHost, cx.s_out));
@@ -232,13 +401,21 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
                 HOST_CUDA(cudaMemcpyAsync(mask + (size_t)f0 * hm * wm, d_mk, (size_t)m * b_m, cudaMemcpyDeviceToHost, cx.s_out));
             }
             HOST_CUDA(cudaEventRecord(cx.ev_out[sl], cx.s_out));
-        }
-        if (bounce_out && it >= 1) {
-            const int pit = it - 1, f0 = pit * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = pit & 1;
-            HOST_CUDA(cudaEventSynchronize(cx.ev_out[sl]));
-            parallel_copy(out_spans(f0, m, cx.h_out[sl]));
+            if (drain) { { std::lock_guard<std::mutex> g(mu); enqueued = it + 1; } cv.notify_all(); }
         }
     }
+    if (drain) {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return drained >= nchunks; });
+        if (drain_rc) HOST_FAIL(CS_ERR_CUDA, "pipeline: download failed");
+    }
+    if (const char* tr = getenv("COMFYSTEREO_HOST_TRACE"))
+        if (atoi(tr))
+            fprintf(stderr, "[cs_host] %d frames, %d chunk(s) of %d, team %d, compact %d, bounce in/out %d/%d: total %.2f ms; "
+                    "consumer waited %.2f ms for downloads, %.2f ms host copy/expand; producer waited %.2f ms for slots\n",
+                    n, nchunks, chunk, team, (int)compact, (int)bounce_in, (int)bounce_out,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - call0).count() * 1e3,
+                    t_event * 1e3, t_host * 1e3, t_slot * 1e3);
     HOST_CUDA(cudaStreamSynchronize(cx.s_in));
     HOST_CUDA(cudaStreamSynchronize(cx.s_run));
     HOST_CUDA(cudaStreamSynchronize(cx.s_out));

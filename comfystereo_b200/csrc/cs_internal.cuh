@@ -194,5 +194,8 @@ struct GpuWarpArgs {
     float* mask;               // [n][h][w]
 };
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s);
+// one channel of each depth output + one byte per mask pixel, for the host transport (cs_host.cu)
+cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,
+                                   float* cdl, float* cdr, uint8_t* cmask, cudaStream_t s);
 
 }  // namespace cs

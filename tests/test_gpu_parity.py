@@ -362,6 +362,24 @@ def test_resized_depth_device_host_and_chunks_agree(gu, oracle, node):
         assert np.array_equal(gu.q8(a), gu.q8(b))
 
 
+def test_host_transport_variants_agree(gu, monkeypatch):
+    """cs_stereo_batch_host moves the depth outputs and the mask either as they are or compacted (one channel / one byte per
+    pixel, re-expanded by host threads), into page-locked or pageable tensors, in several chunks: same bytes every way."""
+    from comfystereo_b200 import engine
+    img = syn.make_image(7, 270, 484, seed=21, black_box=True)
+    dep = syn.make_depth(7, 270, 484, "scene", seed=21)
+    for key, mode, group in (("naive", "left-right", 0), ("gpu_warp", "top-bottom", 3), ("polylines_soft", "red-cyan-anaglyph", 0)):
+        p = engine.make_params(key, mode, 6.0, 0.5, 0.1, 0.5, 2.0, True, 9.0, 20.0, 2.0, 3, group_size=group)
+        ref = [o.cpu() for o in engine.stereo_batch_device(torch.from_numpy(img).cuda(), torch.from_numpy(dep).cuda(), p)]
+        for compact in ("0", "1"):
+            monkeypatch.setenv("COMFYSTEREO_COMPACT_D2H", compact)
+            for pin in (True, False):
+                out = engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), p, device=0, pin_outputs=pin)
+                for a, b in zip(ref, out):
+                    assert torch.equal(a, b), (key, compact, pin)
+    monkeypatch.delenv("COMFYSTEREO_COMPACT_D2H")
+
+
 def test_errors_match_reference(gu, node):
     from comfystereo_b200 import stereoimage_generation as sig
     img = torch.rand(3, 16, 32)
