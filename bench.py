@@ -336,6 +336,11 @@ def main():
         e2e = {"value": world * n * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                "api": "StereoImageNode.generate (CPU tensors in/out) -> cs_stereo_batch_host"}
+        if _lib.lib().cs_host_compact_enabled():
+            # the result tensors hold d2h_bytes_per_step; of those, the depth outputs (3 identical channels) and the
+            # mask (0/1) crossed PCIe as one channel / one byte per pixel and were expanded by host threads
+            e2e["d2h_bus_bytes_per_step"] = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * 4 + int(np.prod(m_shape))
+            e2e["transport"] = "compact depth/mask"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -135,6 +135,12 @@ static int host_share() {
     return std::max(1, (int)hw / peers);
 }
 
+// compact transport of the depth outputs and the mask when the host has the threads to expand them
+static bool compact_transport(int team) {
+    if (const char* e = getenv("COMFYSTEREO_COMPACT_D2H")) return atoi(e) != 0;
+    return team >= 8;
+}
+
 static void parallel_copy(const std::vector<Span>& spans, int team) {
     size_t total = 0;
     for (const auto& s : spans) total += s.bytes;
@@ -225,6 +231,8 @@ using namespace cs;
 
 extern "C" {
 
+int cs_host_compact_enabled(void) { return compact_transport(host_share()) ? 1 : 0; }
+
 void cs_host_release(void) {
     for (int i = 0; i < 16; ++i) {
         std::lock_guard<std::mutex> lk(g_mu[i]);
@@ -262,9 +270,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     const size_t ws_bytes = cs_workspace_bytes(p, chunk, h, w);
     struct Active { Active() { g_active.fetch_add(1); } ~Active() { g_active.fetch_sub(1); } } active;
     const int team = host_share();
-    // compact transport of the depth outputs and the mask when the host has the threads to expand them
-    bool compact = team >= 8;
-    if (const char* e = getenv("COMFYSTEREO_COMPACT_D2H")) compact = atoi(e) != 0;
+    const bool compact = compact_transport(team);
     const bool bounce_in = !(is_pinned(image) && is_pinned(depth));
     const bool stereo_pinned = is_pinned(stereo);
     const bool bounce_out = compact ? !stereo_pinned

@@ -187,6 +187,12 @@ CS_API int cs_stereo_batch_host(const cs_params *p, const float *image, const fl
 /* Frees the device buffers / streams cs_stereo_batch_host caches between calls. */
 CS_API void cs_host_release(void);
 
+/* 1 when cs_stereo_batch_host would currently move the depth outputs (three identical channels) and the
+ * mask (0/1) over PCIe compacted -- one channel, one byte per pixel -- and expand them on the host: it does
+ * when this process may use >= 8 host threads per pipeline (hardware threads / LOCAL_WORLD_SIZE), or as
+ * COMFYSTEREO_COMPACT_D2H=0/1 says.  The tensors the caller receives are the same either way. */
+CS_API int cs_host_compact_enabled(void);
+
 /* Number of kernel launches issued by this library (process-wide) since the last reset
  * (bench.py reports it as gpu_launches). */
 CS_API long long cs_launch_count(int reset);
