@@ -104,14 +104,38 @@ cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, i
 
 // Host transport (cs_host.cu): the depth outputs are three identical channels and the mask is 0/1, so only one
 // channel of each depth output and one byte per mask pixel cross PCIe; the host side re-expands them.
+template <bool DEPTH_U8>   // CPU techniques: the depth outputs are exactly k / 255, so k (one byte) is all that has to travel
 __global__ void __launch_bounds__(256) k_compact_outputs(const float* __restrict__ dl3, const float* __restrict__ dr3,
                                                          const float* __restrict__ mask, int64_t npx, int64_t nmask,
-                                                         float* __restrict__ cdl, float* __restrict__ cdr,
+                                                         void* __restrict__ cdl, void* __restrict__ cdr,
                                                          uint8_t* __restrict__ cmask) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = t0; i < npx; i += stride) { cdl[i] = dl3[3 * i]; cdr[i] = dr3[3 * i]; }
-    // 4 mask pixels per thread (nmask4 words), tail by the first threads
+    if (DEPTH_U8) {
+        // (k / 255.0f) * 255.0f == k exactly for k = 0..255 (checked in tests), 4 pixels per thread
+        uint8_t* bl = (uint8_t*)cdl;
+        uint8_t* br = (uint8_t*)cdr;
+        const int64_t n4 = npx >> 2;
+        for (int64_t i = t0; i < n4; i += stride) {
+            uint32_t a = 0, b = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a |= (uint32_t)(__float2int_rn(dl3[3 * (4 * i + j)] * 255.0f) & 255) << (8 * j);
+                b |= (uint32_t)(__float2int_rn(dr3[3 * (4 * i + j)] * 255.0f) & 255) << (8 * j);
+            }
+            reinterpret_cast<uint32_t*>(bl)[i] = a;
+            reinterpret_cast<uint32_t*>(br)[i] = b;
+        }
+        for (int64_t i = (n4 << 2) + t0; i < npx; i += stride) {
+            bl[i] = (uint8_t)__float2int_rn(dl3[3 * i] * 255.0f);
+            br[i] = (uint8_t)__float2int_rn(dr3[3 * i] * 255.0f);
+        }
+    } else {
+        float* fl = (float*)cdl;
+        float* fr = (float*)cdr;
+        for (int64_t i = t0; i < npx; i += stride) { fl[i] = dl3[3 * i]; fr[i] = dr3[3 * i]; }
+    }
+    // 4 mask pixels per thread, tail by the first threads
     const int64_t n4 = nmask >> 2;
     const bool al = ((uintptr_t)mask % 16 == 0) && ((uintptr_t)cmask % 4 == 0);
     if (al) {
@@ -128,9 +152,10 @@ __global__ void __launch_bounds__(256) k_compact_outputs(const float* __restrict
 }
 
 cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,
-                                   float* cdl, float* cdr, uint8_t* cmask, cudaStream_t s) {
+                                   int depth_u8, void* cdl, void* cdr, uint8_t* cmask, cudaStream_t s) {
     prof_begin(K_MISC, s);
-    k_compact_outputs<<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
+    if (depth_u8) k_compact_outputs<true><<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
+    else k_compact_outputs<false><<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
     prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();

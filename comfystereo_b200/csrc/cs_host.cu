@@ -184,6 +184,22 @@ static void expand3(const float* src, float* dst, size_t p0, size_t p1) {
     for (; i < p1; ++i) { const float v = src[i]; dst[3 * i] = v; dst[3 * i + 1] = v; dst[3 * i + 2] = v; }
 }
 
+// byte k -> k / 255.0f three times (the CPU techniques' depth outputs); lut[k] is the same IEEE division the kernels do
+static void expand3_u8(const uint8_t* src, float* dst, const float* lut, size_t p0, size_t p1) {
+    size_t i = p0;
+#if defined(__SSE2__)
+    for (; i < p1 && ((uintptr_t)(dst + 3 * i) & 15); ++i) { const float v = lut[src[i]]; dst[3 * i] = v; dst[3 * i + 1] = v; dst[3 * i + 2] = v; }
+    for (; i + 4 <= p1; i += 4) {
+        const __m128 v = _mm_set_ps(lut[src[i + 3]], lut[src[i + 2]], lut[src[i + 1]], lut[src[i]]);   // a b c d
+        float* d = dst + 3 * i;
+        _mm_stream_ps(d, _mm_shuffle_ps(v, v, _MM_SHUFFLE(1, 0, 0, 0)));
+        _mm_stream_ps(d + 4, _mm_shuffle_ps(v, v, _MM_SHUFFLE(2, 2, 1, 1)));
+        _mm_stream_ps(d + 8, _mm_shuffle_ps(v, v, _MM_SHUFFLE(3, 3, 3, 2)));
+    }
+#endif
+    for (; i < p1; ++i) { const float v = lut[src[i]]; dst[3 * i] = v; dst[3 * i + 1] = v; dst[3 * i + 2] = v; }
+}
+
 static void expand_mask(const uint8_t* src, float* dst, size_t m0, size_t m1) {
     size_t i = m0;
 #if defined(__SSE2__)
@@ -201,22 +217,28 @@ static void expand_mask(const uint8_t* src, float* dst, size_t m0, size_t m1) {
     for (; i < m1; ++i) dst[i] = (float)src[i];
 }
 
-static void expand_slice(const float* cdl, const float* cdr, const uint8_t* cm, float* dl, float* dr, float* mask,
-                         size_t p0, size_t p1, size_t m0, size_t m1) {
-    expand3(cdl, dl, p0, p1);
-    expand3(cdr, dr, p0, p1);
+static void expand_slice(const void* cdl, const void* cdr, const uint8_t* cm, const float* lut, float* dl, float* dr,
+                         float* mask, size_t p0, size_t p1, size_t m0, size_t m1) {
+    if (lut) {
+        expand3_u8((const uint8_t*)cdl, dl, lut, p0, p1);
+        expand3_u8((const uint8_t*)cdr, dr, lut, p0, p1);
+    } else {
+        expand3((const float*)cdl, dl, p0, p1);
+        expand3((const float*)cdr, dr, p0, p1);
+    }
     expand_mask(cm, mask, m0, m1);
 #if defined(__SSE2__)
     _mm_sfence();
 #endif
 }
 
-static void parallel_expand(const float* cdl, const float* cdr, const uint8_t* cm, float* dl, float* dr, float* mask,
-                            size_t npx, size_t nmask, int team) {
+static void parallel_expand(const void* cdl, const void* cdr, const uint8_t* cm, const float* lut, float* dl, float* dr,
+                            float* mask, size_t npx, size_t nmask, int team) {
     int nt = (int)std::min<size_t>((size_t)std::max(1, std::min(team, 16)), (npx * 24 + nmask * 4) / (4u << 20) + 1);
-    if (nt <= 1) { expand_slice(cdl, cdr, cm, dl, dr, mask, 0, npx, 0, nmask); return; }
+    if (nt <= 1) { expand_slice(cdl, cdr, cm, lut, dl, dr, mask, 0, npx, 0, nmask); return; }
     auto work = [&](int t) {
-        expand_slice(cdl, cdr, cm, dl, dr, mask, npx * t / nt, npx * (t + 1) / nt, nmask * t / nt, nmask * (t + 1) / nt);
+        expand_slice(cdl, cdr, cm, lut, dl, dr, mask, npx * t / nt, npx * (t + 1) / nt, nmask * t / nt,
+                     nmask * (t + 1) / nt);
     };
     std::vector<std::thread> th;
     th.reserve(nt - 1);
@@ -276,7 +298,12 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     const bool bounce_out = compact ? !stereo_pinned
                                     : !(stereo_pinned && is_pinned(depth_l) && is_pinned(depth_r) && is_pinned(mask));
     auto al256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t cmp_depth = al256((size_t)chunk * px * 4), cmp_mask = al256((size_t)chunk * hm * wm);
+    // every CPU technique's depth outputs are exactly k / 255 (wrap quirk Q1): one byte per pixel is enough
+    const bool depth_u8 = compact && p->fill != CS_FILL_GPU_WARP;
+    const size_t dsz = depth_u8 ? 1 : 4;
+    float lut[256];
+    for (int k = 0; k < 256; ++k) lut[k] = (float)k / 255.0f;
+    const size_t cmp_depth = al256((size_t)chunk * px * dsz), cmp_mask = al256((size_t)chunk * hm * wm);
     const size_t cmp_bytes = compact ? 2 * cmp_depth + cmp_mask : 0;
 
     std::lock_guard<std::mutex> lk(g_mu[device]);
@@ -328,8 +355,8 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             const auto c1 = std::chrono::steady_clock::now();
             if (bounce_out) parallel_copy(out_spans(f0, m, cx.h_out[sl]), team);
             if (compact)
-                parallel_expand((const float*)cx.h_cmp[sl], (const float*)(cx.h_cmp[sl] + cmp_depth),
-                                (const uint8_t*)(cx.h_cmp[sl] + 2 * cmp_depth), depth_l + (size_t)f0 * px * 3,
+                parallel_expand(cx.h_cmp[sl], cx.h_cmp[sl] + cmp_depth, (const uint8_t*)(cx.h_cmp[sl] + 2 * cmp_depth),
+                                depth_u8 ? lut : nullptr, depth_l + (size_t)f0 * px * 3,
                                 depth_r + (size_t)f0 * px * 3, mask + (size_t)f0 * hm * wm, (size_t)m * px,
                                 (size_t)m * hm * wm, team);
             const auto c2 = std::chrono::steady_clock::now();
@@ -382,8 +409,8 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             rc = cs_stereo_batch(p, d_img, d_dep, m, h, w, c, d_st, d_dl, d_dr, d_mk, cx.d_ws, cx.ws_bytes, cx.s_run);
             if (rc) { cudaDeviceSynchronize(); return rc; }
             if (compact) {
-                e = launch_compact_outputs(d_dl, d_dr, d_mk, (int64_t)m * px, (int64_t)m * hm * wm,
-                                           (float*)cx.d_cmp[sl], (float*)(cx.d_cmp[sl] + cmp_depth),
+                e = launch_compact_outputs(d_dl, d_dr, d_mk, (int64_t)m * px, (int64_t)m * hm * wm, depth_u8 ? 1 : 0,
+                                           cx.d_cmp[sl], cx.d_cmp[sl] + cmp_depth,
                                            (uint8_t*)(cx.d_cmp[sl] + 2 * cmp_depth), cx.s_run);
                 if (e != cudaSuccess) { cudaDeviceSynchronize(); HOST_FAIL(CS_ERR_CUDA, "compact: %s", cudaGetErrorString(e)); }
             }
@@ -393,8 +420,8 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             if (compact) {
                 float* dst = stereo_pinned ? stereo + (size_t)f0 * ho * wo * 3 : (float*)cx.h_out[sl];
                 HOST_CUDA(cudaMemcpyAsync(dst, d_st, (size_t)m * b_st, cudaMemcpyDeviceToHost, cx.s_out));
-                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl], cx.d_cmp[sl], (size_t)m * px * 4, cudaMemcpyDeviceToHost, cx.s_out));
-                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl] + cmp_depth, cx.d_cmp[sl] + cmp_depth, (size_t)m * px * 4,
+                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl], cx.d_cmp[sl], (size_t)m * px * dsz, cudaMemcpyDeviceToHost, cx.s_out));
+                HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl] + cmp_depth, cx.d_cmp[sl] + cmp_depth, (size_t)m * px * dsz,
                                           cudaMemcpyDeviceToHost, cx.s_out));
                 HOST_CUDA(cudaMemcpyAsync(cx.h_cmp[sl] + 2 * cmp_depth, cx.d_cmp[sl] + 2 * cmp_depth, (size_t)m * hm * wm,
                                           cudaMemcpyDeviceToHost, cx.s_out));

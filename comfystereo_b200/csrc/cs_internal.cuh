@@ -195,7 +195,8 @@ struct GpuWarpArgs {
 };
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s);
 // one channel of each depth output + one byte per mask pixel, for the host transport (cs_host.cu)
+// (depth_u8: the depth outputs are k / 255 -- every CPU technique -- and travel as the byte k)
 cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,
-                                   float* cdl, float* cdr, uint8_t* cmask, cudaStream_t s);
+                                   int depth_u8, void* cdl, void* cdr, uint8_t* cmask, cudaStream_t s);
 
 }  // namespace cs

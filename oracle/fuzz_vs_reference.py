@@ -103,7 +103,48 @@ def main():
             print(f"GPUWARP MISMATCH it={it} seed={seed} shape={(h, w)} div_px={div_px} sep_px={sep_px} expo={expo} "
                   f"conv={conv}: mask {mm}, image err {err:.3g}")
     print("forward_warp_gpu cases", max(1, iters // 4), "mismatching:", gbad)
-    return 1 if (bad or gbad) else 0
+    # the node glue end to end with the blur off (so that everything is exact): modes, balance, pass-through eyes,
+    # masks, depth outputs, sub-batches, depth given as 1 / 3 channels, on the 0..1 or the 0..255 scale, other sizes
+    names = list(oracle.FILL_NAME_TO_KEY)[:8]
+    nbad = 0
+    ncases = max(1, iters // 4)
+    for it in range(ncases):
+        n = int(rng.integers(1, 4))
+        h, w = int(rng.integers(2, 14)), int(rng.integers(4, 90))
+        img = rng.random((n, h, w, 3), dtype=np.float32)
+        if it % 5 == 0:
+            img[:, :, : w // 3] = 0.0
+        ch = int(rng.choice([1, 3]))
+        dh, dw = (h, w) if it % 3 else (int(rng.integers(2, 20)), int(rng.integers(2, 60)))
+        dep = rng.random((n, dh, dw, 1), dtype=np.float32) * np.float32(rng.choice([1.0, 255.0]))
+        dep = np.repeat(dep, ch, axis=-1)
+        if dh != h or dw != w:
+            os.environ["ATEN_CPU_CAPABILITY"] = "default"   # only read at torch start-up: see the resize note in DESIGN.md
+        kw = dict(divergence=float(rng.choice([0.05, 2.0, 4.5, 9.0, 15.0])), separation=float(rng.choice([0.0, 1.5, -3.0])),
+                  modes=str(rng.choice(oracle.MODES[:5])), stereo_balance=float(rng.choice([0.0, 0.5, -0.95, 0.95])),
+                  convergence_point=float(rng.choice([0.0, 0.5, 1.0])), stereo_offset_exponent=float(rng.choice([1.0, 2.0])),
+                  fill_technique=str(rng.choice(names)), depth_blur_edge_threshold=20.0, depth_blur_strength=20.0,
+                  depth_map_blur=False, depth_blur_falloff=2.0, depth_blur_vert_smooth=6, batch_size=int(rng.integers(1, 4)))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = [o.numpy() for o in Node().generate(torch.from_numpy(img), torch.from_numpy(dep), **kw)]
+        got = oracle.node_generate(img, dep, **kw)
+        gw = kw["fill_technique"] == 'GPU Warp (Fast)'
+        resized = (dh, dw) != (h, w)
+        errs = [float(np.abs(a - b).max()) if a.shape == b.shape else float("inf") for a, b in zip(ref, got)]
+        # a resized depth goes through torch's (possibly FMA-contracting) bilinear kernel: not bit-comparable here
+        tol = [2e-5 if gw else 0.0, 1e-6 if gw else 0.0, 1e-6 if gw else 0.0, 0.0]
+        if resized:
+            continue_ok = all(a.shape == b.shape for a, b in zip(ref, got))
+            if not continue_ok:
+                nbad += 1
+                print(f"NODE SHAPE MISMATCH it={it} seed={seed} {kw}")
+            continue
+        if any(e > t for e, t in zip(errs, tol)):
+            nbad += 1
+            print(f"NODE MISMATCH it={it} seed={seed} n={n} h={h} w={w} ch={ch} errs={errs} {kw}")
+    print("node cases", ncases, "mismatching:", nbad)
+    return 1 if (bad or gbad or nbad) else 0
 
 
 if __name__ == "__main__":
