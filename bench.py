@@ -339,7 +339,9 @@ def main():
         if _lib.lib().cs_host_compact_enabled():
             # the result tensors hold d2h_bytes_per_step; of those, the depth outputs (3 identical channels) and the
             # mask (0/1) crossed PCIe as one channel / one byte per pixel and were expanded by host threads
-            e2e["d2h_bus_bytes_per_step"] = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * 4 + int(np.prod(m_shape))
+            # (depth: the byte k of k/255 for the CPU techniques, one float for GPU Warp; mask: one byte)
+            dbytes = 4 if engine.FILL_NAME_TO_KEY.get(args.fill, 'gpu_warp') == 'gpu_warp' else 1
+            e2e["d2h_bus_bytes_per_step"] = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * dbytes + int(np.prod(m_shape))
             e2e["transport"] = "compact depth/mask"
 
     cpu = None
