@@ -92,3 +92,40 @@ def dark_case(seed, h=24, w=333):
     if seed % 3:
         d[:, 150:200] = np.float32(200)
     return img, d
+
+
+def fuzz_case(rng):
+    """One random small stage case (image uint8 [h,w,3], depth 0..255 [h,w], divergence, separation, exponent,
+    convergence) of the kind oracle/fuzz_vs_reference.py and tests/test_gpu_fuzz.py throw at every fill."""
+    h = int(rng.integers(1, 20))
+    w = int(rng.integers(2, 200))
+    style = int(rng.integers(0, 5))
+    if style == 0:      # uniform noise
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    elif style == 1:    # dark: ramps between near-black borders, black pixels that are really there
+        img = rng.integers(0, 3, (h, w, 3), dtype=np.uint8) * rng.integers(0, 2, (h, w, 1), dtype=np.uint8)
+        img[:, ::7] = rng.integers(0, 256, (h, (w + 6) // 7, 3), dtype=np.uint8)
+    elif style == 2:    # mostly black
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, w // 3: w // 3 + 4] = rng.integers(0, 256, 3, dtype=np.uint8)
+    elif style == 3:    # bright (uint8 sums wrap)
+        img = rng.integers(250, 256, (h, w, 3), dtype=np.uint8)
+    else:               # smooth gradient
+        img = np.broadcast_to((np.arange(w) * 255 // max(w - 1, 1)).astype(np.uint8)[None, :, None], (h, w, 3)).copy()
+    dstyle = int(rng.integers(0, 5))
+    if dstyle == 0:
+        d = rng.random((h, w), dtype=np.float32) * np.float32(255)
+    elif dstyle == 1:
+        d = np.broadcast_to(np.linspace(0, 255, w, dtype=np.float32)[None], (h, w)).copy()
+    elif dstyle == 2:
+        d = np.full((h, w), 128, np.float32)
+        d[:, w // 4: w // 2] = 250
+    elif dstyle == 3:
+        d = np.round(rng.random((h, w), dtype=np.float32) * 4) * np.float32(60)
+    else:
+        d = np.full((h, w), 77, np.float32)   # flat
+    div = float(rng.choice([0.5, 2.0, 3.5, 6.0, 10.0, 15.0])) * float(rng.choice([-1, 1]))
+    sep = float(rng.choice([0.0, 0.0, 1.0, -2.5]))
+    expo = float(rng.choice([1.0, 2.0, 0.7]))
+    conv = float(rng.choice([0.0, 0.5, 1.0, 0.3]))
+    return img, d.astype(np.float32), div, sep, expo, conv
