@@ -44,7 +44,7 @@ __device__ __forceinline__ float gw_pow(float ab, float expo) {  // torch.pow sp
     return powf(ab, expo);
 }
 
-__global__ void __launch_bounds__(256) k_gpuwarp(const GpuWarpArgs a) {
+__global__ void __launch_bounds__(512) k_gpuwarp(const GpuWarpArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
     const int nwords = (w + 31) >> 5;
@@ -296,7 +296,9 @@ cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_gpuwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_begin(K_GPUWARP, s);
-    k_gpuwarp<<<dim3(a.h, a.n), 256, smem, s>>>(a);
+    // a row's shared memory (25 B per column) limits the CTAs per SM: keep ~32 warps resident by widening the CTA
+    const int threads = (smem > 56 * 1024) ? 512 : 256;
+    k_gpuwarp<<<dim3(a.h, a.n), threads, smem, s>>>(a);
     prof_end(K_GPUWARP, s);
     count_launch();
     return cudaGetLastError();
