@@ -44,7 +44,7 @@ __device__ __forceinline__ double hy_u8(uint32_t v) {
     return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 }
 
-__global__ void __launch_bounds__(256) k_hybrid_splat(const WarpArgs a) {
+__global__ void __launch_bounds__(512) k_hybrid_splat(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
     if (a.eye[eye].passthrough) return;
@@ -185,7 +185,7 @@ cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_hybrid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prof_begin(K_HYBRID_SPLAT, s);
-    k_hybrid_splat<<<dim3(a.h, a.n, 2), 256, smem, s>>>(a);
+    k_hybrid_splat<<<dim3(a.h, a.n, 2), smem > 56 * 1024 ? 512 : 256, smem, s>>>(a);   // wide rows: see launch_warp_rows
     prof_end(K_HYBRID_SPLAT, s);
     count_launch();
     cudaError_t e = cudaGetLastError();

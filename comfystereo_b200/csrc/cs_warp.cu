@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t interp_px(int x, int xl, int xr, int w, uint
 }
 
 template <int FILL>  // CS_FILL_NONE / NAIVE / NAIVE_INTERP / INVERSE / NONE_POST / INVERSE_POST
-__global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
+__global__ void __launch_bounds__(512) k_warp_rows(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
     if (a.eye[eye].passthrough) return;
@@ -304,44 +304,32 @@ __global__ void __launch_bounds__(256) k_warp_rows(const WarpArgs a) {
     }
 }
 
+// a wide row's shared memory limits the CTAs per SM: keep the SM's warp slots busy with wider CTAs then
+static int row_threads(size_t smem) { return smem > 56 * 1024 ? 512 : 256; }
+
+template <int FILL>
+static void launch_rows_as(const WarpArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(k_warp_rows<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_warp_rows<FILL><<<grid, row_threads(smem), smem, s>>>(a);
+}
+
 cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
     dim3 grid(a.h, a.n, 2);
-    size_t smem;
     const size_t simg = ((size_t)a.w * 4 + 15) & ~(size_t)15;   // staged RGBX8 row
+    const size_t base = simg + (size_t)a.w * 4 + nwords * 4;     // + winners + filled bitmap
+    if (base + (size_t)a.w * 4 + nwords * 4 > 227 * 1024) return cudaErrorInvalidValue;
     prof_begin(K_WARP_ROWS, s);
     switch (a.fill) {
-        case CS_FILL_NONE:
-            smem = simg + (size_t)a.w * 4 + nwords * 4;
-            k_warp_rows<CS_FILL_NONE><<<grid, 256, smem, s>>>(a);
-            break;
-        case CS_FILL_NAIVE:
-            smem = simg + (size_t)a.w * 4 + nwords * 4;
-            k_warp_rows<CS_FILL_NAIVE><<<grid, 256, smem, s>>>(a);
-            break;
-        case CS_FILL_NAIVE_INTERP:
-            smem = simg + (size_t)a.w * 8 + nwords * 8;
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_warp_rows<CS_FILL_NAIVE_INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_warp_rows<CS_FILL_NAIVE_INTERP><<<grid, 256, smem, s>>>(a);
-            break;
-        case CS_FILL_NONE_POST:
-            smem = simg + (size_t)a.w * 4 + nwords * 4;
-            k_warp_rows<CS_FILL_NONE_POST><<<grid, 256, smem, s>>>(a);
-            break;
-        case CS_FILL_INVERSE_POST:
-            smem = simg + (size_t)a.w * 8 + nwords * 4;
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_warp_rows<CS_FILL_INVERSE_POST><<<grid, 256, smem, s>>>(a);
-            break;
-        case CS_FILL_INVERSE:
-            smem = simg + (size_t)a.w * 8;
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_warp_rows<CS_FILL_INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_warp_rows<CS_FILL_INVERSE><<<grid, 256, smem, s>>>(a);
-            break;
+        case CS_FILL_NONE: launch_rows_as<CS_FILL_NONE>(a, grid, base, s); break;
+        case CS_FILL_NAIVE: launch_rows_as<CS_FILL_NAIVE>(a, grid, base, s); break;
+        case CS_FILL_NAIVE_INTERP: launch_rows_as<CS_FILL_NAIVE_INTERP>(a, grid, base + (size_t)a.w * 4 + nwords * 4, s); break;
+        case CS_FILL_NONE_POST: launch_rows_as<CS_FILL_NONE_POST>(a, grid, base, s); break;
+        case CS_FILL_INVERSE_POST: launch_rows_as<CS_FILL_INVERSE_POST>(a, grid, simg + (size_t)a.w * 8 + nwords * 4, s); break;
+        case CS_FILL_INVERSE: launch_rows_as<CS_FILL_INVERSE>(a, grid, simg + (size_t)a.w * 8, s); break;
         default:
+            prof_end(K_WARP_ROWS, s);
             return cudaErrorInvalidValue;
     }
     prof_end(K_WARP_ROWS, s);

@@ -198,3 +198,18 @@ def test_4k_polylines_sharp_natural_tiles(node, oracle):
     want = oracle.node_generate(img, dep, **p)
     for g, w_ in zip(got, want):
         assert np.array_equal(q8(g), q8(w_))
+
+
+@pytest.mark.parametrize("fill", ["none", "naive", "naive_interpolating", "inverse", "hybrid_edge", "none_post", "inverse_post"])
+def test_very_wide_rows(oracle, fill):
+    """Rows of 7700 columns: one row's shared memory leaves room for two CTAs per SM, so the row kernels run with 512-thread
+    CTAs there (launch_warp_rows / launch_hybrid); same results as the oracle."""
+    import gpu_util as gu
+    rng = np.random.default_rng(77)
+    for h, w in ((3, 7700), (2, 15990)):     # 15990: close to the 16000-column capacity of these techniques
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        d = (syn.make_depth(1, h, w, "scene", seed=5, channels=1)[0, ..., 0] * np.float32(255)).astype(np.float32)
+        got = gu.warp_fill(img, d, fill, 1.5, 0.2, 2.0, 0.5)[..., :3]
+        want = oracle.apply_stereo_divergence(img, d, 1.5, 0.2, 2.0, fill, 0.5)
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= (1 if fill == "hybrid_edge" else 0), (fill, w, int((diff > 0).sum()))
