@@ -438,7 +438,7 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     {
         const bool sharp = p->fill == CS_FILL_POLYLINES_SHARP;
         const bool soft = p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_HYBRID_EDGE_PLUS;
-        const int wmax = sharp ? 8000 : (soft ? 12000 : (p->fill == CS_FILL_GPU_WARP ? 9500 : 16000));
+        const int wmax = sharp ? 8000 : (soft ? 12000 : (p->fill == CS_FILL_GPU_WARP ? 9000 : 16000));
         if (w > wmax)
             return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
                         "(one row per CTA in shared memory)", w, wmax);

@@ -213,3 +213,32 @@ def test_very_wide_rows(oracle, fill):
         want = oracle.apply_stereo_divergence(img, d, 1.5, 0.2, 2.0, fill, 0.5)
         diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
         assert diff.max() <= (1 if fill == "hybrid_edge" else 0), (fill, w, int((diff > 0).sum()))
+
+
+@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 8000), ("Fill - Polylines Soft", 12000),
+                                       ("GPU Warp (Fast)", 9000), ("Fill - Naive", 16000),
+                                       ("Imperfect fill - Hybrid Edge", 16000)])
+def test_row_capacity_limits(oracle, fill, wmax):
+    """One row (or tile) lives in a CTA's shared memory, so every technique has a documented maximum width: at the limit
+    the node still matches the oracle, one step beyond it the library refuses up front (CS_ERR_UNSUPPORTED)."""
+    from comfystereo_b200 import StereoImageNode
+    from comfystereo_b200._lib import CsError
+    node = StereoImageNode()
+    kw = dict(divergence=2.0, separation=0.0, modes="left-right", stereo_balance=0.0, convergence_point=0.5,
+              stereo_offset_exponent=2.0, fill_technique=fill, depth_blur_edge_threshold=20.0, depth_blur_strength=8.0,
+              depth_map_blur=True, depth_blur_falloff=2.0, depth_blur_vert_smooth=2, batch_size=2)
+    h = 2
+    img = syn.make_image(1, h, wmax, seed=9)
+    dep = syn.make_depth(1, h, wmax, "scene", seed=9, channels=1)
+    got = [o.numpy() for o in node.generate(torch.from_numpy(img), torch.from_numpy(dep), **kw)]
+    want = oracle.node_generate(img, dep, **kw)
+    if fill == "GPU Warp (Fast)":
+        assert np.array_equal(got[3], want[3]) and np.abs(got[0] - want[0]).max() <= 1e-6
+    else:
+        q = lambda a: np.rint(a * 255.0).astype(np.int32)
+        assert np.abs(q(got[0]) - q(want[0])).max() <= (1 if "Hybrid" in fill else 0)
+        assert np.array_equal(got[3], want[3]) or "Hybrid" in fill
+    img2 = np.zeros((1, h, wmax + 8, 3), np.float32)
+    dep2 = np.zeros((1, h, wmax + 8, 1), np.float32)
+    with pytest.raises(CsError, match="exceeds"):
+        node.generate(torch.from_numpy(img2), torch.from_numpy(dep2), **kw)
