@@ -449,7 +449,9 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     if (per == 0 || workspace_bytes < per)
         return fail(CS_ERR_WORKSPACE, "cs_stereo_batch: workspace %zu B < %zu B needed for %d frame(s)", workspace_bytes, per, group);
     int chunk = group;
-    while (chunk + group <= n && cs_workspace_bytes(p, chunk + group, h, w) <= workspace_bytes) chunk += group;
+    // (frames are a grid dimension of every kernel: stay well inside its 65535 limit)
+    while (chunk + group <= n && chunk + group <= 16384 && cs_workspace_bytes(p, chunk + group, h, w) <= workspace_bytes)
+        chunk += group;
     int ho, wo, hm, wm;
     cs_output_dims(p, h, w, &ho, &wo, &hm, &wm);
     cudaStream_t s = (cudaStream_t)stream;
