@@ -56,6 +56,23 @@ def test_product_never_imports_the_oracle():
                     f"{f}: {line.strip()}"
 
 
+def test_compact_transport_policy(monkeypatch):
+    """The host path compacts the depth outputs / mask on the bus only when it may use >= 8 host threads per pipeline
+    (hardware threads / LOCAL_WORLD_SIZE); COMFYSTEREO_COMPACT_D2H overrides.  Pure host logic: no GPU needed."""
+    lib = _lib.lib()
+    hw = len(os.sched_getaffinity(0))     # what std::thread::hardware_concurrency() reports
+    monkeypatch.delenv("COMFYSTEREO_COMPACT_D2H", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert lib.cs_host_compact_enabled() == (1 if hw >= 8 else 0)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(max(hw, 1)))      # one thread per rank: never
+    assert lib.cs_host_compact_enabled() == 0
+    monkeypatch.setenv("COMFYSTEREO_COMPACT_D2H", "1")
+    assert lib.cs_host_compact_enabled() == 1
+    monkeypatch.setenv("COMFYSTEREO_COMPACT_D2H", "0")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert lib.cs_host_compact_enabled() == 0
+
+
 def test_params_follow_python_rounding():
     # bs = int(round(s)) is banker's rounding, R = int(s) truncates (SIG:1208-1209, quirk Q11)
     for s, bs, r in ((2.5, 2, 2), (3.5, 4, 3), (20.5, 20, 20), (21.5, 22, 21), (20.0, 20, 20), (0.7, 1, 0)):
