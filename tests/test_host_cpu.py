@@ -31,6 +31,12 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().cs_abi_version() == 2
 
 
+def test_graft_entry_build():
+    """The driver's build check: compiles (no-op when up to date), loads the library, checks the ABI version."""
+    import __graft_entry__ as g
+    g.build()
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
