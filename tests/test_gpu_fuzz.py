@@ -55,3 +55,20 @@ def test_random_forward_warp_cases(gu, oracle, seed):
             assert np.abs(warped[0].transpose(2, 0, 1) - ow).max() <= 1e-6
         else:
             assert (mask[0] != om.astype(bool)).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("sep", [-5.0, 5.0])
+def test_large_separation(gu, oracle, sep):
+    """Separation at the widget's limits pushes ~40 columns of points off one side of a 795-pixel row: far more segments
+    than usual are alive at the first / last output column (the reference's fixed-size active list overflows there --
+    DESIGN.md section 7 -- so the oracle, which has no such capacity, is the yardstick)."""
+    rng = np.random.default_rng(8)
+    h, w = 3, 795
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for kind in ("quant", "noise"):
+        d = (syn.make_depth(1, h, w, kind, seed=4, channels=1)[0, ..., 0] * np.float32(255)).astype(np.float32)
+        for fill in FILLS:
+            got = gu.warp_fill(img, d, fill, -1.0, sep, 2.0, 1.0)[..., :3]
+            want = oracle.apply_stereo_divergence(img, d, -1.0, sep, 2.0, fill, 1.0)
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert diff.max() <= (1 if fill.startswith('hybrid') else 0), (kind, fill, int((diff > 0).sum()))

@@ -59,6 +59,23 @@ def test_blur_stage(gu, oracle, spec):
     assert mm[0, 0] == L.min() and mm[0, 1] == L.max() and mm[0, 2] == R.min() and mm[0, 3] == R.max()
 
 
+@pytest.mark.parametrize("case", [(96, 640, 'scene', 200, 60, 4.0, 15), (96, 640, 'scene', 100.5, 0.1, 0.5, 3),
+                                  (40, 24, 'scene', 33, 20, 2.0, 6), (64, 300, 'steps', 1.0, 20, 1.0, 0),
+                                  (64, 300, 'scene', 0.7, 20, 2.0, 2), (64, 300, 'noise', 1.5, 5, 3.0, 1),
+                                  (30, 700, 'card', 150, 10, 2.0, 10), (1, 5, 'noise', 20, 20, 2.0, 6),
+                                  (300, 1, 'noise', 4, 2, 1.0, 15)])
+def test_blur_parameter_extremes(gu, oracle, case):
+    """The widget ranges' corners (strength 200 / vert 15 / falloff 4 / threshold 60 and 0.1), a box wider than the image,
+    strength 0.7 (box 1, radius 0: the reference's 0/0 weights give NaN, quirk Q11), one-row and one-column images:
+    CUDA == oracle bit for bit, NaNs included.  (The oracle was checked against the reference's torch blur on the same
+    cases in the build container: <= 4e-5 on the 0..255 scale, identical NaN pattern.)"""
+    h, w, kind, s, thr, fo, v = case
+    d = (syn.make_depth(1, h, w, kind, seed=3, channels=1)[0, ..., 0] * np.float32(255)).astype(np.float32)
+    L, R, mm = gu.blur(d, s, thr, fo, v)
+    oL, oR = oracle.blur(d, s, thr, fo, v)
+    assert np.array_equal(L, oL, equal_nan=True) and np.array_equal(R, oR, equal_nan=True)
+
+
 @pytest.mark.parametrize("spec", STAGE["warp"], ids=[s["name"] + "_" + s["kind"] + "_" + s["fill"] for s in STAGE["warp"]])
 def test_warp_stage(gu, spec):
     """apply_stereo_divergence on the index-probe image: R + 256 G - 1 is the source column, so equality
