@@ -30,6 +30,9 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 namespace cs {
 
@@ -110,6 +113,17 @@ static cudaError_t ctx_ensure(HostCtx& c, int device, size_t in_bytes, size_t ou
     c.bounce_in_bytes = (bounce_in || keep_in) ? in_bytes : 0;
     c.bounce_out_bytes = (bounce_out || keep_out) ? out_bytes : 0;
     return cudaSuccess;
+}
+
+// Fresh pageable result tensors are first touched by this library: ask for huge pages so that the first touch costs one
+// fault per 2 MB instead of one per 4 KB (a hint; ignored when transparent huge pages are off).
+static void hint_huge_pages(void* p, size_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    const uintptr_t a = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)p + bytes) & ~(uintptr_t)4095;
+    if (b > a + (4u << 20)) (void)madvise((void*)a, b - a, MADV_HUGEPAGE);
+#else
+    (void)p; (void)bytes;
+#endif
 }
 
 static bool is_pinned(const void* p) {
@@ -297,6 +311,10 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     const bool stereo_pinned = is_pinned(stereo);
     const bool bounce_out = compact ? !stereo_pinned
                                     : !(stereo_pinned && is_pinned(depth_l) && is_pinned(depth_r) && is_pinned(mask));
+    if (!stereo_pinned) hint_huge_pages(stereo, (size_t)n * b_st);
+    if (!is_pinned(depth_l)) hint_huge_pages(depth_l, (size_t)n * b_d);
+    if (!is_pinned(depth_r)) hint_huge_pages(depth_r, (size_t)n * b_d);
+    if (!is_pinned(mask)) hint_huge_pages(mask, (size_t)n * b_m);
     auto al256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // every CPU technique's depth outputs are exactly k / 255 (wrap quirk Q1): one byte per pixel is enough
     const bool depth_u8 = compact && p->fill != CS_FILL_GPU_WARP;
