@@ -397,6 +397,28 @@ def test_host_transport_variants_agree(gu, monkeypatch):
     monkeypatch.delenv("COMFYSTEREO_COMPACT_D2H")
 
 
+def test_integration_stub_runs_as_documented(gu, node):
+    """INTEGRATION.md shows the ctypes stub a maintainer of the reference would add; run that very text (library path and
+    the reference's own fill-name table filled in) and compare with the node, once with a depth batch of another size."""
+    import os
+    import re
+    from conftest import ROOT
+    from comfystereo_b200 import _lib, engine
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(.*?)```", text, re.S).group(1).replace("/path/to/libcomfystereo_b200.so", _lib.LIB_PATH)
+    ns = {"fill_technique_mapping": dict(engine.FILL_NAME_TO_KEY)}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    img = syn.make_image(3, 40, 96, seed=31)
+    for dshape, fill in (((40, 96), "Fill - Polylines Sharp"), ((25, 61), "GPU Warp (Fast)"), ((40, 96), "Fill - Naive")):
+        dep = syn.make_depth(3, dshape[0], dshape[1], "scene", seed=31)
+        args = (torch.from_numpy(img), torch.from_numpy(dep), 4.5, 0.5, "top-bottom", 0.1, 0.5, 2.0, fill, 20.0, 7.0, True,
+                2.0, 3, 2)
+        want = node.generate(*args)
+        got = ns["generate"](None, *args)
+        for a, b in zip(want, got):
+            assert torch.equal(a, b), fill
+
+
 def test_errors_match_reference(gu, node):
     from comfystereo_b200 import stereoimage_generation as sig
     img = torch.rand(3, 16, 32)
