@@ -89,8 +89,15 @@ __device__ __forceinline__ uint32_t interp_px(int x, int xl, int xr, int w, uint
     return o;
 }
 
+// Register budget per variant (measured): the sweep-only variants run fastest compiled for up to 512 threads (40
+// registers), the ones with a second pass over the row (interpolating fill, z-buffer) with the 256-thread budget.
+template <int FILL>
+constexpr int rows_max_threads() {
+    return (FILL == CS_FILL_NAIVE_INTERP || FILL == CS_FILL_INVERSE || FILL == CS_FILL_INVERSE_POST) ? 256 : 512;
+}
+
 template <int FILL>  // CS_FILL_NONE / NAIVE / NAIVE_INTERP / INVERSE / NONE_POST / INVERSE_POST
-__global__ void __launch_bounds__(512) k_warp_rows(const WarpArgs a) {
+__global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
     if (a.eye[eye].passthrough) return;
@@ -311,7 +318,8 @@ template <int FILL>
 static void launch_rows_as(const WarpArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_warp_rows<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_warp_rows<FILL><<<grid, row_threads(smem), smem, s>>>(a);
+    const int threads = row_threads(smem) < rows_max_threads<FILL>() ? row_threads(smem) : rows_max_threads<FILL>();
+    k_warp_rows<FILL><<<grid, threads, smem, s>>>(a);
 }
 
 cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s) {
