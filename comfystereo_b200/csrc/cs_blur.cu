@@ -147,7 +147,7 @@ constexpr int kRowPad = 16;
 // Rows outside the image hold weight 0: fmaf(0, wv, acc) == acc, which is the reference's zero padding.
 // Tap order (ascending, fmaf) is the oracle's, so the result is bit-identical to it.
 template <int V>   // vertical smoothing radius (0..15): compile-time so that the column walk unrolls without predicates
-__global__ void __launch_bounds__(kSeg) k_blur_blend(
+__global__ void __launch_bounds__(kSeg, 4) k_blur_blend(
     const float* __restrict__ gray, FrameStats* __restrict__ st, int scale_mode, int group, int n,
     int h, int w, int bs, int radius, const __grid_constant__ BlurLut lut,
     const uint8_t* __restrict__ dist_l, const uint8_t* __restrict__ dist_r, float* __restrict__ blur_l,
