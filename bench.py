@@ -126,6 +126,7 @@ def cpu_baseline(args, frames):
     the host cores, `frames` frames of the benchmark workload.  One untimed call first (page-in, thread pool)."""
     import oracle as orc
     orc.lib()
+    orc.set_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     img, dep = make_frames(frames, args.height, args.width, seed=100)
     params = dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence)
     orc.node_generate(img[:1], dep[:1], **params)
@@ -139,7 +140,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    import oracle as orc
+    cores = orc.set_threads(len(os.sched_getaffinity(0)))   # the threads the OpenMP loops really get
     sample = args.cpu_frames
     times = []
     for i in range(args.warmup + args.steps):
@@ -347,7 +349,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt = cpu_baseline(args, args.cpu_frames)
-        cpu = {"value": val, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+        import oracle as orc
+        cpu = {"value": val, "unit": "frames/s", "cores": orc.set_threads(0), "kind": "port",
                "sample": f"{args.cpu_frames} frame(s) of the same workload, oracle/stereo_oracle.c with OpenMP over rows, "
                          f"{dt:.2f} s"}
 

@@ -56,6 +56,13 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """Sets (n > 0) and returns the number of host threads the oracle's OpenMP loops use."""
+    f = lib().orc_set_threads
+    f.restype = ctypes.c_int
+    return int(f(ctypes.c_int(int(n))))
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
