@@ -10,9 +10,11 @@
 // page-locked bounce buffers (one per slot and direction) and moves data between them and the caller's memory
 // with a team of host threads, overlapped with the GPU work of the neighbouring chunks.
 // The depth outputs are three identical channels and the mask is 0/1: when the host has threads to spare, only
-// one channel of each depth output and one byte per mask pixel cross PCIe (a small kernel compacts them) and the
-// thread team expands them into the caller's tensors while the next chunk is in flight -- 70 MB instead of 116 MB
-// per 1080p side-by-side frame on the bus that bounds this call.
+// one channel of each depth output (the byte k of k/255 for the CPU techniques, one float for GPU Warp) and one
+// byte per mask pixel cross PCIe (a small kernel compacts them), and a consumer thread's team expands them into
+// the caller's tensors with non-temporal stores while later chunks are in flight -- 58 MB instead of 116 MB per
+// 1080p side-by-side frame.  Whatever needs host work after the download (bounce copy, expansion) is done by that
+// consumer thread, in chunk order, so the producer only ever waits for a free slot.
 // Device buffers, bounce buffers and streams are cached per device; cs_host_release() frees them.
 #include <algorithm>
 #include <atomic>
