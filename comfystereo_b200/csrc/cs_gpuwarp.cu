@@ -44,7 +44,8 @@ __device__ __forceinline__ float gw_pow(float ab, float expo) {  // torch.pow sp
     return powf(ab, expo);
 }
 
-__global__ void __launch_bounds__(512) k_gpuwarp(const GpuWarpArgs a) {
+template <int TPB>   // CTA size the kernel is compiled for (register budget): 256, or 512 for rows that leave room for two CTAs per SM
+__global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
     const int nwords = (w + 31) >> 5;
@@ -293,12 +294,15 @@ cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
     size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8 + (size_t)a.w + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(k_gpuwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prof_begin(K_GPUWARP, s);
     // a row's shared memory (25 B per column) limits the CTAs per SM: keep ~32 warps resident by widening the CTA
-    const int threads = (smem > 56 * 1024) ? 512 : 256;
-    k_gpuwarp<<<dim3(a.h, a.n), threads, smem, s>>>(a);
+    const bool wide = smem > 56 * 1024;
+    if (smem > 48 * 1024) {
+        if (wide) cudaFuncSetAttribute(k_gpuwarp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(k_gpuwarp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    prof_begin(K_GPUWARP, s);
+    if (wide) k_gpuwarp<512><<<dim3(a.h, a.n), 512, smem, s>>>(a);
+    else k_gpuwarp<256><<<dim3(a.h, a.n), 256, smem, s>>>(a);
     prof_end(K_GPUWARP, s);
     count_launch();
     return cudaGetLastError();
