@@ -44,7 +44,8 @@ __device__ __forceinline__ double hy_u8(uint32_t v) {
     return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
 }
 
-__global__ void __launch_bounds__(512) k_hybrid_splat(const WarpArgs a) {
+template <int TPB>   // CTA size the kernel is compiled for: 256, or 512 for very wide rows (see launch_warp_rows)
+__global__ void __launch_bounds__(TPB) k_hybrid_splat(const WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
     if (a.eye[eye].passthrough) return;
@@ -182,10 +183,14 @@ __global__ void __launch_bounds__(256) k_hybrid_gapfill(const WarpArgs a, double
 
 cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
     size_t smem = (size_t)a.w * 12 + (size_t)((a.w + 31) / 32) * 8 + 16;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(k_hybrid_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool wide = smem > 56 * 1024;
+    if (smem > 48 * 1024) {
+        if (wide) cudaFuncSetAttribute(k_hybrid_splat<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(k_hybrid_splat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     prof_begin(K_HYBRID_SPLAT, s);
-    k_hybrid_splat<<<dim3(a.h, a.n, 2), smem > 56 * 1024 ? 512 : 256, smem, s>>>(a);   // wide rows: see launch_warp_rows
+    if (wide) k_hybrid_splat<512><<<dim3(a.h, a.n, 2), 512, smem, s>>>(a);
+    else k_hybrid_splat<256><<<dim3(a.h, a.n, 2), 256, smem, s>>>(a);
     prof_end(K_HYBRID_SPLAT, s);
     count_launch();
     cudaError_t e = cudaGetLastError();
