@@ -483,8 +483,8 @@ __device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* im
 // tile (|shift| <= reach_px[eye], plus a guard band) and sweeps only its own output columns.  Everything that decides
 // a centre inside the tile -- the segments active there, their sorted order -- lies inside the window, so the result is
 // the whole-row result; the artificial sentinel segments at the window's ends only cover columns outside the tile.
-template <int PER>
-__global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a, int sharp, int* __restrict__ row_flags,
+template <int PER, bool SHARP>   // SHARP: polylines_sharp (two points per source pixel), compile-time
+__global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a, int* __restrict__ row_flags,
                                                                int* __restrict__ status, int tile_w, int tile_ext,
                                                                double reach0, double reach1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
         if (s0 + w > W) s0 = W - w;
     }
     RowCtx c;
-    c.w = w; c.sharp = sharp != 0; c.npts = (sharp ? 2 * w : w) + 2; c.nsg = c.npts - 1;
+    c.w = w; c.sharp = SHARP; c.npts = (SHARP ? 2 * w : w) + 2; c.nsg = c.npts - 1;
     const int npts = c.npts, nsg = c.nsg;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* px = reinterpret_cast<float*>(smem_raw);                 // [NP]
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
             double cx = ((double)(col + s0) + 0.5) + cd;
             cx = cx + sep_px;
             clo[col + 1] = (float)fabs(cd);
-            if (c.sharp) {
+            if (SHARP) {
                 px[1 + 2 * col] = (float)(cx - 0.45);
                 px[2 + 2 * col] = (float)(cx + 0.45);
             } else {
@@ -762,8 +762,8 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
                 const float bv = px[sidx[k + 1]];
                 const int spA = (int)sidx[k - o1], spB = (int)sidx[k - o2];
                 const float ax0 = px[spA], ax1 = px[spA + 1], bx0 = px[spB], bx1 = px[spB + 1];
-                const float aq0 = clo[pt_slot(spA, c.sharp)], aq1 = clo[pt_slot(spA + 1, c.sharp)];
-                const float bq0 = clo[pt_slot(spB, c.sharp)], bq1 = clo[pt_slot(spB + 1, c.sharp)];
+                const float aq0 = clo[pt_slot(spA, SHARP)], aq1 = clo[pt_slot(spA + 1, SHARP)];
+                const float bq0 = clo[pt_slot(spB, SHARP)], bq1 = clo[pt_slot(spB + 1, SHARP)];
                 const float ad = ax1 - ax0, bd = bx1 - bx0;
                 // ip < 1 is guaranteed when the centre stays more than half a float32 ulp of (x1 - x0) below x1:
                 // always for lengths < 2 (the centre is >= 1e-7 below the interval's end), else when x1 is far enough
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     ctx.t0 = t0;
     uint32_t* out = a.out[eye] + row_off + t0;
     bool give_up = false;
-    const bool shp = c.sharp;
+    constexpr bool shp = SHARP;
     // warps take 32-column blocks from a shared counter: blocks inside folds cost several times more than smooth ones
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
     for (;;) {
@@ -884,10 +884,12 @@ template <int PER>
 static cudaError_t launch_fast(const WarpArgs& a, int sharp, int* flags, int* status, int wmax, int tile_w, int tile_ext,
                                int ntiles, double reach0, double reach1, cudaStream_t s) {
     const size_t fs = fast_smem_per<PER>(wmax);
-    cudaError_t e = cudaFuncSetAttribute(k_polylines<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
+    cudaError_t e = sharp ? cudaFuncSetAttribute(k_polylines<PER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs)
+                          : cudaFuncSetAttribute(k_polylines<PER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
     if (e != cudaSuccess) return e;
     prof_begin(K_POLY_FAST, s);
-    k_polylines<PER><<<dim3(a.h, a.n, 2 * ntiles), kPolyThreads, fs, s>>>(a, sharp, flags, status, tile_w, tile_ext, reach0, reach1);
+    if (sharp) k_polylines<PER, true><<<dim3(a.h, a.n, 2 * ntiles), kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1);
+    else k_polylines<PER, false><<<dim3(a.h, a.n, 2 * ntiles), kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1);
     prof_end(K_POLY_FAST, s);
     count_launch();
     return cudaGetLastError();
