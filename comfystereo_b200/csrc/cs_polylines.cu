@@ -483,7 +483,7 @@ __device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* im
 // tile (|shift| <= reach_px[eye], plus a guard band) and sweeps only its own output columns.  Everything that decides
 // a centre inside the tile -- the segments active there, their sorted order -- lies inside the window, so the result is
 // the whole-row result; the artificial sentinel segments at the window's ends only cover columns outside the tile.
-template <int PER, bool SHARP>   // SHARP: polylines_sharp (two points per source pixel), compile-time
+template <int PER, bool SHARP, bool TILED>   // compile-time: polylines_sharp (two points per source pixel); tiles of a wide row
 __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a, int* __restrict__ row_flags,
                                                                int* __restrict__ status, int tile_w, int tile_ext,
                                                                double reach0, double reach1) {
@@ -495,7 +495,8 @@ __global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a,
     // In tile mode the buckets start tile_ext columns left of the tile so that a list replay (quirk Q7) can walk back
     // through a whole fold to the nearest visit with a single active segment.
     int t0 = 0, tw = W, own = W, s0 = 0, w = W;
-    if (tile_w > 0) {
+    if (!TILED) tile_w = 0;
+    if (TILED) {
         const int o0 = tile * tile_w;
         own = min(tile_w, W - o0);
         t0 = max(o0 - tile_ext, 0);
@@ -884,12 +885,16 @@ template <int PER>
 static cudaError_t launch_fast(const WarpArgs& a, int sharp, int* flags, int* status, int wmax, int tile_w, int tile_ext,
                                int ntiles, double reach0, double reach1, cudaStream_t s) {
     const size_t fs = fast_smem_per<PER>(wmax);
-    cudaError_t e = sharp ? cudaFuncSetAttribute(k_polylines<PER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs)
-                          : cudaFuncSetAttribute(k_polylines<PER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
+    const void* fn = tile_w > 0 ? (sharp ? (const void*)k_polylines<PER, true, true> : (const void*)k_polylines<PER, false, true>)
+                                : (sharp ? (const void*)k_polylines<PER, true, false> : (const void*)k_polylines<PER, false, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
     if (e != cudaSuccess) return e;
     prof_begin(K_POLY_FAST, s);
-    if (sharp) k_polylines<PER, true><<<dim3(a.h, a.n, 2 * ntiles), kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1);
-    else k_polylines<PER, false><<<dim3(a.h, a.n, 2 * ntiles), kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1);
+    const dim3 grid(a.h, a.n, 2 * ntiles);
+#define CS_POLY_LAUNCH(SH, TL) k_polylines<PER, SH, TL><<<grid, kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1)
+    if (tile_w > 0) { if (sharp) CS_POLY_LAUNCH(true, true); else CS_POLY_LAUNCH(false, true); }
+    else { if (sharp) CS_POLY_LAUNCH(true, false); else CS_POLY_LAUNCH(false, false); }
+#undef CS_POLY_LAUNCH
     prof_end(K_POLY_FAST, s);
     count_launch();
     return cudaGetLastError();
