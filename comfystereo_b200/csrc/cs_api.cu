@@ -170,9 +170,6 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
     EyeSpec eye[2];
     eye_specs(p, w, eye);
     CS_CUDA(launch_init_stats(ws.stats, n, s), "init_stats");
-    if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP)
-        CS_CUDA(cudaMemsetAsync((char*)ws.warp_scratch + ws.warp_scratch_bytes - 16 * sizeof(int), 0, 16 * sizeof(int), s),
-                "memset status");
     // N1 resize: depth frames of another size become a 1-channel gray depth at image size first
     if (needs_resize(p, h, w)) {
         CS_CUDA(launch_resize_gray(depth, n, p->depth_h, p->depth_w, c, h, w, ws.resized, s), "resize");
@@ -474,16 +471,12 @@ int cs_polylines_status(const cs_params* p, int chunk, int h, int w, const void*
     if (!p || !workspace) return fail(CS_ERR_ARG, "cs_polylines_status: bad argument");
     Workspace ws = carve(p, chunk, h, w, const_cast<void*>(workspace));
     if (!ws.warp_scratch) return fail(CS_ERR_ARG, "cs_polylines_status: not a polylines configuration");
-    const size_t nflags = (size_t)chunk * 2 * h;
-    int* host = (int*)malloc((nflags + 16) * sizeof(int));
-    if (!host) return fail(CS_ERR_ARG, "out of host memory");
-    cudaError_t e = cudaMemcpy(host, ws.warp_scratch, (nflags + 16) * sizeof(int), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { free(host); return cuda_fail(e, "cudaMemcpy"); }
-    int cnt = 0;
-    for (size_t i = 0; i < nflags; ++i) cnt += host[i] != 0;
-    if (status_out) *status_out = host[nflags];
-    if (flagged_rows) *flagged_rows = cnt;
-    free(host);
+    // scratch layout (cs_polylines.cu): [0] status bits, [1] rows listed for the sequential kernel, ...
+    int host[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(host, ws.warp_scratch, sizeof(host), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    if (status_out) *status_out = host[0];
+    if (flagged_rows) *flagged_rows = host[1];
     return CS_OK;
 }
 

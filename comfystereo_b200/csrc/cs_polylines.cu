@@ -1,35 +1,39 @@
 // cs_polylines.cu -- P: apply_stereo_divergence_polylines (SIG:1912-1992), soft and sharp.
 //
-// One CTA per (row, frame, eye); the whole row lives in shared memory.  Two kernels:
+// k_polylines<NW, SHARP>   one CTA of NW warps per (tile of output columns, row, frame, eye).  A tile's CTA builds the
+//   sorted point table of the SOURCE window that can reach its columns and sweeps only those columns; a row narrow
+//   enough is one tile.  Thread t owns 8 consecutive points (4 source columns sharp / 8 soft) in registers from the
+//   depth load to the sorted scatter:
+//   A points   coord_d in FP64, x = col + 0.5 + coord_d + sep rounded to float32, closeness |coord_d|; sharp emits
+//              x -+ 0.45; sentinels (-W, 0) and (2W, 0)                                                   SIG:1919-1936
+//   B,C sort   the reference's stable insertion sort (SIG:1941-1946) without sorting: shifts are bounded, so the table is
+//              nearly sorted.  Prefix-max / suffix-min scans tell every point whether anything before it is larger or
+//              anything after it smaller; if not, its rank is its index.  Inversions within two positions (depth jitter
+//              swaps neighbours) are counted in registers; deeper ones (folds) go to a work list.
+//   D sets     rank space: END[k] = rank of the end point of the segment starting at sorted point k, REACH = its prefix
+//              maximum.  A segment j <= k is active strictly inside interval (k, k+1) iff END[j] > k -- integer
+//              compares.  Intervals nobody reaches into have their own segment as the only candidate; the others go to
+//              a work list and are resolved to one or two candidates (cs_poly_core.cuh classify_interval).
+//   E sweep    thread per output column, float32 with a certified error bound (fast_column); the ~0.3 % of columns it
+//              cannot certify are redone at once with the reference's exact FP64 / float32 rounding sequence and list
+//              replay (exact_column).  Rows whose replay gives up are listed for k_polylines_exact.
 //
-// k_polylines<PER>  the fast path (rows up to ~4090 px sharp / ~8190 px soft)
-//   A points   thread per source column: coord_d in FP64, x = col + 0.5 + coord_d + sep rounded to float32,
-//              closeness |coord_d| float32; sharp emits x -+ 0.45.  Sentinels (-W, 0) and (2W, 0).   SIG:1919-1936
-//   B,C sort   the reference's stable insertion sort by x (SIG:1941-1946) without sorting: shifts are bounded, so the
-//              table is nearly sorted.  Two CTA scans (prefix max / suffix min in source order) tell every point
-//              whether anything before it is larger or anything after it smaller; if not, its rank is its source
-//              index.  The others go to a work list and count their inversions in the window the scans bound.
-//   D,D2 sets  the reference's "active list" at a centre is the SET of segments with x0 < ctr <= x1.  A prefix max
-//              of segment ends (sorted order) bounds the search.  Per sorted interval the set is constant; intervals
-//              with one candidate, or two whose order cannot change inside the interval, are resolved here.
-//   E sweep    thread per output column; the sub-intervals of column c are (pred, b0), (b0, b1), ... of the sorted
-//              points in bucket c (SIG:1955-1961).  Selection and colour accumulation reproduce the reference's
-//              FP64 / float32 rounding sequence.  Choices that depend on the ORDER of the reference's append /
-//              swap-remove list (exact ties, no valid candidate -- quirk Q7) are replayed from the nearest visit
-//              with a single active segment; if that does not fit its budget the row is redone by
-//              sequential_row(), one thread replaying the reference's sweep bit for bit.
-//
-// k_polylines_exact  counting sort + one-thread sequential sweep for every row: serves rows too wide for the fast
-//              kernel's tables and is the independent cross-check of the fast path in the tests.
+// k_polylines_exact   counting sort + one-thread sequential sweep per listed row (or every row: test hook, and
+//   disparity ranges too large for a useful tile).
 //
 // Bytes per pixel and eye: depth 4 B + RGBX8 4 B read (L2-resident scratch), RGBX8 4 B written.
+#include <cstdlib>
+
 #include "cs_internal.cuh"
+#include "cs_poly_core.cuh"
 
 namespace cs {
 
 namespace {
 
-constexpr int kPolyThreads = 512;
+using poly::Tab;
+
+constexpr int kExactThreads = 512;
 constexpr double kEps = 1e-7;
 
 struct RowCtx {
@@ -47,9 +51,6 @@ __device__ __forceinline__ float pt_clo(int i, const RowCtx& c, const float* clo
     if (i <= 0 || i >= c.npts - 1) return 0.0f;
     return clo[c.sharp ? ((i - 1) >> 1) : (i - 1)];
 }
-// branch-free variants on a table padded with the two sentinels: clo2[0] = 0, clo2[1 + col], clo2[w + 1] = 0
-__device__ __forceinline__ int pt_slot(int i, bool sharp) { return sharp ? ((i + 1) >> 1) : i; }
-__device__ __forceinline__ int slot_col(int slot, int w) { return min(max(slot - 1, 0), w - 1); }
 
 __device__ __forceinline__ Normalizer pl_normalizer(const WarpArgs& a, int eye, int frame, float* scale_out) {
     const FrameStats st = a.stats[frame];
@@ -66,10 +67,13 @@ __device__ __forceinline__ Normalizer pl_normalizer(const WarpArgs& a, int eye, 
     return make_normalizer(lo, hi, scale, a.conv);
 }
 
-// CTA-wide exclusive scan of cnt[0..n) in place (n arbitrary), returns nothing; blockDim = kPolyThreads.
+// exponents other than 1 and 2: kept out of line so that the unrolled point loop stays small
+__device__ __noinline__ double pow_general(double a, double e) { return pow(a, e); }
+
+// CTA-wide exclusive scan of cnt[0..n) in place (n arbitrary); blockDim = kExactThreads.
 __device__ void cta_exclusive_scan(int* cnt, int n, int* s_warp) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (n + kPolyThreads - 1) / kPolyThreads;
+    const int per = (n + kExactThreads - 1) / kExactThreads;
     const int b0 = tid * per, b1 = min(b0 + per, n);
     int sum = 0;
     for (int i = b0; i < b1; ++i) sum += cnt[i];
@@ -81,13 +85,13 @@ __device__ void cta_exclusive_scan(int* cnt, int n, int* s_warp) {
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        int v = (lane < kPolyThreads / 32) ? s_warp[lane] : 0;
+        int v = (lane < kExactThreads / 32) ? s_warp[lane] : 0;
         int vi = v;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, vi, o);
             if (lane >= o) vi += t;
         }
-        if (lane < kPolyThreads / 32) s_warp[lane] = vi - v;
+        if (lane < kExactThreads / 32) s_warp[lane] = vi - v;
     }
     __syncthreads();
     int run = s_warp[wid] + inc - sum;
@@ -95,12 +99,7 @@ __device__ void cta_exclusive_scan(int* cnt, int n, int* s_warp) {
     __syncthreads();
 }
 
-// Builds the point table and its stable sort.  On return (after a barrier):
-//   px[i]     float32 x of source point i                         [npts]
-//   clo[col]  float32 closeness of source column col              [w]
-//   sidx[k]   source point index of the k-th point in sorted order [npts]
-//   start[b]  rank of the first point of bucket b, b = floor(x)+1 clamped to [0, w+1];  start[w+2] = npts
-// tmp is a scratch array of npts uint16.
+// Builds the point table of a whole row and its stable sort (counting sort by floor(x), then rank inside the bucket).
 __device__ void build_sorted_points(const WarpArgs& a, int eye, int frame, int y, const RowCtx& c,
                                     float* px, float* clo, unsigned short* sidx, unsigned short* tmp,
                                     unsigned short* rnk, int* start, int* s_warp) {
@@ -130,7 +129,6 @@ __device__ void build_sorted_points(const WarpArgs& a, int eye, int frame, int y
         }
     }
     __syncthreads();
-    // histogram; slot order inside a bucket is arbitrary here
     for (int i = threadIdx.x; i < npts; i += blockDim.x) {
         float fl = floorf(px[i]);
         int b = (fl < 0.0f) ? 0 : ((fl >= (float)w) ? w + 1 : (int)fl + 1);
@@ -144,7 +142,6 @@ __device__ void build_sorted_points(const WarpArgs& a, int eye, int frame, int y
         tmp[start[b] + rnk[i]] = (unsigned short)i;
     }
     __syncthreads();
-    // rank inside the bucket by (x, source index): equals the reference's stable insertion sort
     for (int i = threadIdx.x; i < npts; i += blockDim.x) {
         float xi = px[i];
         float fl = floorf(xi);
@@ -164,8 +161,7 @@ __device__ void build_sorted_points(const WarpArgs& a, int eye, int frame, int y
 }
 
 // colour accumulation of one sub-interval, SIG:1981-1989 (float32 accumulator, float64 terms)
-__device__ __forceinline__ void accumulate(float* color, uint32_t pl, uint32_t pr, bool same, double ip,
-                                           double sig) {
+__device__ __forceinline__ void accumulate(float* color, uint32_t pl, uint32_t pr, bool same, double ip, double sig) {
     if (same) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -187,15 +183,17 @@ __device__ __forceinline__ void accumulate(float* color, uint32_t pl, uint32_t p
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// exact sweep: one thread replays the reference's list semantics
+// sequential sweep: one thread replays the reference's list semantics for a whole row
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPolyThreads) k_polylines_exact(const WarpArgs a, int sharp, int act_cap,
-                                                                  const int* __restrict__ row_flags,
-                                                                  int* __restrict__ status) {
+// row_list == nullptr: every (frame, eye, row); else the rows k_polylines listed (row id = (frame * 2 + eye) * h + y).
+__global__ void __launch_bounds__(kExactThreads) k_polylines_exact(const WarpArgs a, int sharp, int act_cap,
+                                                                   const int* __restrict__ row_list,
+                                                                   const int* __restrict__ row_count,
+                                                                   int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int w = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z;
-    if (a.eye[eye].passthrough) return;
-    if (row_flags && !row_flags[((int64_t)frame * 2 + eye) * a.h + y]) return;
+    __shared__ int s_warp[32];
+    const int w = a.w;
+    const int total = row_list ? *row_count : a.n * 2 * a.h;
     RowCtx c;
     c.w = w; c.sharp = sharp != 0; c.npts = (sharp ? 2 * w : w) + 2; c.nsg = c.npts - 1;
     const int npts = c.npts, nsg = c.nsg;
@@ -206,672 +204,441 @@ __global__ void __launch_bounds__(kPolyThreads) k_polylines_exact(const WarpArgs
     unsigned short* tmp = sidx + (npts + (npts & 1));
     unsigned short* rnk = tmp + (npts + (npts & 1));
     unsigned short* act = rnk + (npts + (npts & 1));   // [act_cap] source point indices of active segments
-    __shared__ int s_warp[32];
-    build_sorted_points(a, eye, frame, y, c, px, clo, sidx, tmp, rnk, start, s_warp);
-
-    if (threadIdx.x != 0) return;
-    const int64_t row_off = (int64_t)frame * a.h * w + (int64_t)y * w;
-    const uint32_t* img = a.image_u8 + row_off;
-    uint32_t* out = a.out[eye] + row_off;
-    int nact = 0, sgp = 0, pi = 0;
-    bool overflow = false;
-    for (int col = 0; col < w; ++col) {
-        float color[3] = {0.5f, 0.5f, 0.5f};
-        while ((double)px[sidx[pi]] < (double)col) ++pi;
-        --pi;
-        while ((double)px[sidx[pi]] < (double)(col + 1)) {
-            double pa = (double)px[sidx[pi]], pb = (double)px[sidx[pi + 1]];
-            double from = fmax((double)col, pa) + kEps;
-            double to = fmin((double)(col + 1), pb) - kEps;
-            double sig = to - from;
-            double ctr = from + 0.5 * sig;
-            while (sgp < nsg && (double)px[sidx[sgp]] < ctr) {
-                if (nact < act_cap) act[nact++] = sidx[sgp];
-                else overflow = true;
-                ++sgp;
-            }
-            for (int i = 0; i < nact;) {
-                if ((double)px[act[i] + 1] < ctr) { act[i] = act[nact - 1]; --nact; }
-                else ++i;
-            }
-            int best = 0;
-            if (nact != 1) {
-                double bestc = -kEps;
-                for (int i = 0; i < nact; ++i) {
-                    int sp = act[i];
-                    float x0 = px[sp], x1 = px[sp + 1];
-                    float den = x1 - x0;
-                    double ip = (ctr - (double)x0) / (double)den;
-                    double t0 = (1.0 - ip) * (double)pt_clo(sp, c, clo), t1 = ip * (double)pt_clo(sp + 1, c, clo);
-                    double cl = t0 + t1;
-                    if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+        const int rowid = row_list ? row_list[idx] : idx;
+        const int y = rowid % a.h, fe = rowid / a.h, eye = fe & 1, frame = fe >> 1;
+        if (a.eye[eye].passthrough) continue;
+        build_sorted_points(a, eye, frame, y, c, px, clo, sidx, tmp, rnk, start, s_warp);
+        if (threadIdx.x == 0) {
+            const int64_t row_off = (int64_t)frame * a.h * w + (int64_t)y * w;
+            const uint32_t* img = a.image_u8 + row_off;
+            uint32_t* out = a.out[eye] + row_off;
+            int nact = 0, sgp = 0, pi = 0;
+            bool overflow = false;
+            for (int col = 0; col < w; ++col) {
+                float color[3] = {0.5f, 0.5f, 0.5f};
+                while ((double)px[sidx[pi]] < (double)col) ++pi;
+                --pi;
+                while ((double)px[sidx[pi]] < (double)(col + 1)) {
+                    double pa = (double)px[sidx[pi]], pb = (double)px[sidx[pi + 1]];
+                    double from = fmax((double)col, pa) + kEps;
+                    double to = fmin((double)(col + 1), pb) - kEps;
+                    double sig = to - from;
+                    double ctr = from + 0.5 * sig;
+                    while (sgp < nsg && (double)px[sidx[sgp]] < ctr) {
+                        if (nact < act_cap) act[nact++] = sidx[sgp];
+                        else overflow = true;
+                        ++sgp;
+                    }
+                    for (int i = 0; i < nact;) {
+                        if ((double)px[act[i] + 1] < ctr) { act[i] = act[nact - 1]; --nact; }
+                        else ++i;
+                    }
+                    int best = 0;
+                    if (nact != 1) {
+                        double bestc = -kEps;
+                        for (int i = 0; i < nact; ++i) {
+                            int sp = act[i];
+                            float x0 = px[sp], x1 = px[sp + 1];
+                            float den = x1 - x0;
+                            double ip = (ctr - (double)x0) / (double)den;
+                            double t0 = (1.0 - ip) * (double)pt_clo(sp, c, clo), t1 = ip * (double)pt_clo(sp + 1, c, clo);
+                            double cl = t0 + t1;
+                            if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
+                        }
+                    }
+                    if (nact > 0) {
+                        int sp = act[best];
+                        int cl = pt_col(sp, c), cr = pt_col(sp + 1, c);
+                        double ip = 0.0;
+                        if (cl != cr) {
+                            float den = px[sp + 1] - px[sp];
+                            ip = (ctr - (double)px[sp]) / (double)den;
+                        }
+                        accumulate(color, img[cl], img[cr], cl == cr, ip, sig);
+                    }
+                    ++pi;
                 }
+                out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
             }
-            if (nact > 0) {
-                int sp = act[best];
-                int cl = pt_col(sp, c), cr = pt_col(sp + 1, c);
-                double ip = 0.0;
-                if (cl != cr) {
-                    float den = px[sp + 1] - px[sp];
-                    ip = (ctr - (double)px[sp]) / (double)den;
-                }
-                accumulate(color, img[cl], img[cr], cl == cr, ip, sig);
-            }
-            ++pi;
+            if (overflow) atomicOr(status, 1);
         }
-        out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
+        __syncthreads();
     }
-    if (overflow) atomicOr(status, 1);
 }
 
 // ------------------------------------------------------------------------------------------
-// fast sweep
+// tile kernel
 // ------------------------------------------------------------------------------------------
-// Conversions between float32 and float64 (F2F / I2F) issue on the 16-lane XU pipe and were the
-// bottleneck of the first version of this kernel (ncu: xu pipe saturated, fp64 pipe 12 % busy).
-// The hot loop therefore never converts: the sorted coordinates are widened once per point, uint8
-// colours are widened with a 2^52 bias trick, and float64 sums are rounded to float32 precision on
-// the FP64 pipe.
-
-// Round-to-nearest of a float64 to 24 significant bits, result kept as float64: equals
-// (double)(float)x whenever (float)x is a normal float32.  Veltkamp / Dekker split with 2^29 + 1
-// (three FP64 operations).  It differs from IEEE round-half-even only on exact ties (low 29 bits
-// = 100...0), which an accumulated colour sum hits with probability 2^-29 per operation.
-__device__ __forceinline__ double round24_fp(double x) {
-    const double g = x * 536870913.0;
-    const double d = x - g;
-    return g + d;
-}
-// The same rounding with exact IEEE ties-to-even, in integer arithmetic.  Used where ties are NOT improbable: the
-// float32 subtraction x1 - x0 of two float32 coordinates is a short exact binary number, and when it needs 25 bits
-// (small coordinates, first columns of a row) it is an exact tie half of the time.
-__device__ __forceinline__ double round24_even(double x) {
-    uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
-    uint32_t nlo = lo + 0x0FFFFFFFu + ((lo >> 29) & 1u);
-    hi += (nlo < lo) ? 1u : 0u;
-    return __hiloint2double((int)hi, (int)(nlo & 0xE0000000u));
-}
-// uint8 -> float64 without I2F: 2^52 + v is exact, subtracting 2^52 leaves v
-__device__ __forceinline__ double u8_to_f64(uint32_t v) {
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-}
-
-struct PolyCtx {
-    const float* px;        // [npts] source-order x (float32)
-    const double* sxd;      // [npts] sorted x, widened
-    const unsigned short* sidx;   // [npts] sorted rank -> source point index
-    const float* reach;     // [npts] prefix max (sorted order) of segment ends
-    const float* clo;       // [w + 2] padded: clo[pt_slot(i)] is the closeness of source point i
-    const int* start;       // [tw+3] first sorted rank of bucket b = floor(x) - t0 + 1
-    int t0;                 // first output column of the tile (0 when the CTA owns the whole row)
-    RowCtx row;             // describes the tile's SOURCE window: w = window width, points / segments of the window
+struct PolyGeom {             // per eye
+    int tile_w[2];            // output columns per tile (>= W: the row is one tile and the window is the whole row)
+    int ext[2];               // buckets start this many columns left of the tile (list replays walk back through a fold)
+    int ntiles[2];
+    int lo_off[2], hi_off[2]; // source window of bucket columns [t0, t0 + tw): [t0 + lo_off, t0 + tw + hi_off) clipped to the row
 };
-// cand[k] (k = sorted rank, uint16): bits 0-1 number of segments active anywhere strictly inside the interval
-// (sorted point k, sorted point k+1), 3 = "three or more / does not fit"; bits 2-8 and 9-15: how many ranks back the
-// first / second active segment starts.  Kept apart from sidx[] so that the threads resolving intervals (writers of
-// cand) never touch words other threads are reading (sidx) -- racecheck-clean.
-constexpr int kOff1Shift = 2, kOff2Shift = 9;
 
-// `col` is the output column relative to the tile
-__device__ __forceinline__ double visit_ctr(const PolyCtx& c, int col, int k, double* sig_out) {
-    double pa = c.sxd[k], pb = c.sxd[k + 1];
-    double from = fmax((double)(col + c.t0), pa) + kEps;
-    double to = fmin((double)(col + c.t0 + 1), pb) - kEps;
-    double sig = to - from;
-    *sig_out = sig;
-    return from + 0.5 * sig;
-}
+template <int NW, bool SHARP>
+struct PolyLayout {
+    static constexpr int NT = NW * 32, NP = NT * 8, CPT = SHARP ? 4 : 8, SCAP = NT * CPT;
+    static constexpr size_t kBytes = 4 * (size_t)(NP + 8) + 4 * (size_t)NP + 4 * (size_t)NP + 2 * 4 * (size_t)(SCAP + 8) +
+                                     8 * (size_t)NT + 2 * (size_t)NP + 2 * (size_t)(NP + 16) + 2 * (size_t)NP +
+                                     2 * (size_t)(SCAP + 8);
+    // source columns a CTA can take: every point incl. both sentinels fits the NP slots (4 columns of slack for the
+    // 16-byte alignment of the window's first column)
+    static constexpr int kCapCols = (NP - 2) / (SHARP ? 2 : 1) - 4;
+};
 
-// number of active segments at ctr (interval k); *which = sorted index of the last one found
-__device__ __forceinline__ int active_count(const PolyCtx& c, int k, double ctr, int* which) {
-    int n = 0;
-    for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
-        int sp = (int)c.sidx[j];
-        if (!(c.sxd[j] < ctr) || ((double)c.px[sp + 1] < ctr)) continue;
-        ++n;
-        *which = j;
-    }
-    return n;
-}
-
-// The reference's selection when the result depends on the ORDER of its active list (quirk Q7):
-// find the nearest earlier visit with exactly one active segment (there the list is [that segment],
-// whatever happened before), replay the append / swap-remove list from there to the target visit,
-// then choose as the reference does.  Returns the source point index of the chosen segment, or -1
-// when the replay does not fit its budget (the whole row is then redone sequentially).
-__device__ __noinline__ int replay_choice(const PolyCtx& c, int col, int k) {
-    constexpr int kCap = 64, kBudget = 6000;
-    unsigned short lst[kCap];
-    const int nsg = c.row.nsg;
-    // ---- backward: locate the reset visit
-    int rc = col, rk = k, sgp = 0, steps = 0;
-    bool from_row_start = false;
-    while (true) {
-        // previous visit
-        if (rk > c.start[rc + 1] - 1) --rk;
-        else if (rc > 0) { --rc; rk = c.start[rc + 2] - 1; }
-        else if (c.t0 == 0) { from_row_start = true; break; }
-        else return -1;   // the history continues left of this tile: the whole row is replayed instead
-        if (++steps > kBudget) return -1;
-        double sig;
-        double ctr = visit_ctr(c, rc, rk, &sig);
-        int which = 0;
-        if (active_count(c, rk, ctr, &which) == 1) { sgp = which; break; }
-    }
-    int n = 0;
-    if (from_row_start) { rc = 0; rk = c.start[1] - 1; sgp = 0; }
-    // ---- forward: replay list maintenance up to and including the target visit
-    while (true) {
-        double sig;
-        double ctr = visit_ctr(c, rc, rk, &sig);
-        while (sgp < nsg && c.sxd[sgp] < ctr) {
-            if (n >= kCap) return -1;
-            lst[n++] = c.sidx[sgp];
-            ++sgp;
-        }
-        for (int i = 0; i < n;) {
-            if ((double)c.px[lst[i] + 1] < ctr) { lst[i] = lst[n - 1]; --n; }
-            else ++i;
-        }
-        if (rc == col && rk == k) {
-            if (n == 0) return -1;
-            int best = 0;
-            if (n != 1) {
-                double bestc = -kEps;
-                for (int i = 0; i < n; ++i) {
-                    int sp = lst[i];
-                    float x0 = c.px[sp], x1 = c.px[sp + 1];
-                    float den = x1 - x0;
-                    double ip = (ctr - (double)x0) / (double)den;
-                    double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
-                    double cl = t0 + t1;
-                    if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
-                }
-            }
-            return lst[best];
-        }
-        // next visit
-        if (rk < c.start[rc + 2] - 1) ++rk;
-        else { ++rc; rk = c.start[rc + 1] - 1; }
-    }
-}
-
-// Any visit that is not "exactly one active segment, the one starting at the interval's left point":
-// builds the active set, selects in FP64 like the reference, and resolves order-dependent choices by replay.
-// Returns the source point index of the chosen segment (-1: nothing active), -2: give up (row flagged).
-__device__ __noinline__ int general_visit(const PolyCtx& c, int col, int k, double ctr) {
-    int nact = 0, best = -1, only = -1, nbest = 0;
-    double bestc = -kEps;
-    for (int j = k; j >= 0 && !((double)c.reach[j] < ctr); --j) {
-        int sp = (int)c.sidx[j];
-        float x0 = c.px[sp], x1 = c.px[sp + 1];
-        if (!((double)x0 < ctr) || ((double)x1 < ctr)) continue;
-        ++nact;
-        only = sp;
-        float den = x1 - x0;
-        double ip = (ctr - (double)x0) / (double)den;
-        double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
-        double cl = t0 + t1;
-        if (0.0 < ip && ip < 1.0) {
-            if (bestc < cl) { bestc = cl; best = sp; nbest = 1; }
-            else if (bestc == cl) ++nbest;
-        }
-    }
-    if (nact == 0) return -1;
-    if (nact == 1) return only;
-    if (best >= 0 && nbest == 1) return best;
-    int r = replay_choice(c, col, k);
-    return r < 0 ? -2 : r;
-}
-
-// The reference's sequential sweep (SIG:1948-1991) over one row whose sorted point table is in shared
-// memory; run by ONE thread.  act: scratch for the active list (capacity act_cap).
-__device__ __noinline__ bool sequential_row(const PolyCtx& c, const uint32_t* img, uint32_t* out,
-                                            unsigned short* act, int act_cap) {
-    const int w = c.row.w, nsg = c.row.nsg;
-    int nact = 0, sgp = 0, pi = 0;
-    bool overflow = false;
-    for (int col = 0; col < w; ++col) {
-        float color[3] = {0.5f, 0.5f, 0.5f};
-        while (c.sxd[pi] < (double)col) ++pi;
-        --pi;
-        while (c.sxd[pi] < (double)(col + 1)) {
-            double sig;
-            double ctr = visit_ctr(c, col, pi, &sig);
-            while (sgp < nsg && c.sxd[sgp] < ctr) {
-                if (nact < act_cap) act[nact++] = c.sidx[sgp];
-                else overflow = true;
-                ++sgp;
-            }
-            for (int i = 0; i < nact;) {
-                if ((double)c.px[act[i] + 1] < ctr) { act[i] = act[nact - 1]; --nact; }
-                else ++i;
-            }
-            int best = 0;
-            if (nact != 1) {
-                double bestc = -kEps;
-                for (int i = 0; i < nact; ++i) {
-                    int sp = act[i];
-                    float x0 = c.px[sp], x1 = c.px[sp + 1];
-                    float den = x1 - x0;
-                    double ip = (ctr - (double)x0) / (double)den;
-                    double t0 = (1.0 - ip) * (double)c.clo[pt_slot(sp, c.row.sharp)], t1 = ip * (double)c.clo[pt_slot(sp + 1, c.row.sharp)];
-                    double cl = t0 + t1;
-                    if (bestc < cl && 0.0 < ip && ip < 1.0) { bestc = cl; best = i; }
-                }
-            }
-            if (nact > 0) {
-                int sp = act[best];
-                int cl = pt_col(sp, c.row), cr = pt_col(sp + 1, c.row);
-                double ip = 0.0;
-                if (cl != cr) {
-                    float den = c.px[sp + 1] - c.px[sp];
-                    ip = (ctr - (double)c.px[sp]) / (double)den;
-                }
-                accumulate(color, img[cl], img[cr], cl == cr, ip, sig);
-            }
-            ++pi;
-        }
-        out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
-    }
-    return overflow;
-}
-
-// One CTA per (row, frame, eye), 512 threads, PER points per thread (512 * PER >= points of the row).
-// tile_w == 0: the CTA owns the whole row.  tile_w > 0 (rows too wide for the shared-memory tables): blockIdx.z also
-// enumerates tiles of tile_w output columns; the CTA builds the point table of the SOURCE window that can reach its
-// tile (|shift| <= reach_px[eye], plus a guard band) and sweeps only its own output columns.  Everything that decides
-// a centre inside the tile -- the segments active there, their sorted order -- lies inside the window, so the result is
-// the whole-row result; the artificial sentinel segments at the window's ends only cover columns outside the tile.
-template <int PER, bool SHARP, bool TILED>   // compile-time: polylines_sharp (two points per source pixel); tiles of a wide row
-__global__ void __launch_bounds__(kPolyThreads, 2) k_polylines(const WarpArgs a, int* __restrict__ row_flags,
-                                                               int* __restrict__ status, int tile_w, int tile_ext,
-                                                               double reach0, double reach1) {
+template <int NW, bool SHARP, int TPS>   // TPS: resident threads per SM the register budget is set for
+__global__ void __launch_bounds__(NW * 32, TPS / (NW * 32))
+k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int* __restrict__ row_list,
+            int* __restrict__ counters, int mode_flags) {
+    using L = PolyLayout<NW, SHARP>;
+    constexpr int NT = L::NT, NP = L::NP, CPT = L::CPT, SCAP = L::SCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NP = kPolyThreads * PER;
-    const int W = a.w, y = blockIdx.x, frame = blockIdx.y, eye = blockIdx.z & 1, tile = blockIdx.z >> 1;
-    if (a.eye[eye].passthrough) return;
-    // t0 / tw: origin and width of the column range the point buckets cover; the sweep writes its last `own` columns.
-    // In tile mode the buckets start tile_ext columns left of the tile so that a list replay (quirk Q7) can walk back
-    // through a whole fold to the nearest visit with a single active segment.
-    int t0 = 0, tw = W, own = W, s0 = 0, w = W;
-    if (!TILED) tile_w = 0;
-    if (TILED) {
-        const int o0 = tile * tile_w;
-        own = min(tile_w, W - o0);
-        t0 = max(o0 - tile_ext, 0);
-        tw = o0 + own - t0;
-        const double sep = a.eye[eye].sep_px, rch = (eye ? reach1 : reach0) + 4.0;
-        const double lo = floor((double)t0 - sep - rch), hi = ceil((double)(t0 + tw) - sep + rch);
-        s0 = (int)fmax(lo, 0.0);
-        const int s1 = (int)fmin(hi, (double)W);
-        w = max(s1 - s0, 1);
-        if (s0 + w > W) s0 = W - w;
-    }
-    RowCtx c;
-    c.w = w; c.sharp = SHARP; c.npts = (SHARP ? 2 * w : w) + 2; c.nsg = c.npts - 1;
-    const int npts = c.npts, nsg = c.nsg;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    float* px = reinterpret_cast<float*>(smem_raw);                 // [NP]
-    double* sxd = reinterpret_cast<double*>(px + NP);               // [NP]   (aliases pm / sm during the sort)
-    float* pm = reinterpret_cast<float*>(sxd);                      // [NP] inclusive prefix max of px
-    float* sm = pm + NP;                                            // [NP] inclusive suffix min of px
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(sxd + NP);   // [NP] sorted rank -> source point
-    unsigned short* cand = sidx + NP;                                     // [NP] per-interval candidate code
-    float* reach = reinterpret_cast<float*>(cand + NP);             // [NP]
-    float* clo = reach + NP;                                        // [w + 2] padded closeness table
-    int* start = reinterpret_cast<int*>(clo + (w + 4));             // [w + 4]
-    uint32_t* simg = reinterpret_cast<uint32_t*>(start + (w + 4));  // [w]
-    unsigned short* tlist = reinterpret_cast<unsigned short*>(simg + w);  // [NP] sorted intervals with two active segments
-    __shared__ float s_wa[16], s_wb[16];
-    __shared__ int s_flag, s_ndirty, s_ntwo, s_next;
-    if (tid == 0) { s_flag = 0; s_ndirty = 0; s_ntwo = 0; s_next = 0; }
-    // during the sort the reach[] region holds the list of out-of-order points and their ranks (uint16 each)
-    unsigned short* dlist = reinterpret_cast<unsigned short*>(reach);
-    unsigned short* drank = dlist + NP;
+    const int W = a.w, tile = blockIdx.x, y = blockIdx.y, frame = blockIdx.z >> 1, eye = blockIdx.z & 1;
+    if (a.eye[eye].passthrough || tile >= g.ntiles[eye]) return;
 
-    // ---- A: image row, points
-    const int64_t row_off = (int64_t)frame * a.h * W + (int64_t)y * W;
+    // ---- geometry: own output columns [o0, o0 + own), buckets [t0, t0 + tw), source window [s0, s0 + w)
+    int t0 = 0, tw = W, own = W, s0 = 0, w = W;
+    if (g.tile_w[eye] < W) {
+        const int o0 = tile * g.tile_w[eye];
+        own = min(g.tile_w[eye], W - o0);
+        t0 = max(o0 - g.ext[eye], 0);
+        tw = o0 + own - t0;
+        s0 = min(max(t0 + g.lo_off[eye], 0), W - 1) & ~3;
+        w = min(max(t0 + tw + g.hi_off[eye], s0 + 1), W) - s0;
+    }
+    const int npts = (SHARP ? 2 * w : w) + 2, nsg = npts - 1;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+
+    float* XA = reinterpret_cast<float*>(smem_raw);             // [NP + 8]  x in source order; X[1] is 16-byte aligned
+    float* X = XA + 3;
+    float* SX = XA + NP + 8;                                     // [NP]      x in sorted order
+    uint32_t* ER = reinterpret_cast<uint32_t*>(SX + NP);         // [NP]      END | REACH << 16
+    float* QA = reinterpret_cast<float*>(ER + NP);               // [SCAP + 8] closeness, padded by one on either side
+    float* Q = QA + 3;
+    uint32_t* IMGA = reinterpret_cast<uint32_t*>(QA + SCAP + 8); // [SCAP + 8] RGBX, padded the same way
+    uint32_t* IMGP = IMGA + 3;
+    float* TMX = reinterpret_cast<float*>(IMGA + SCAP + 8);      // [NT] max of every point up to the end of thread t's
+    float* TMN = TMX + NT;                                       // [NT] min of every point from the start of thread t's
+    uint16_t* SID = reinterpret_cast<uint16_t*>(TMN + NT);       // [NP]
+    uint16_t* WSP = SID + NP;                                    // [NP + 16] (holds the source-order ranks during the sort)
+    uint16_t* RNK = WSP + 7;                                     //           RNK[1] is 16-byte aligned
+    uint16_t* LIST = WSP + NP + 16;                              // [NP] work lists: deep inversions, then hard intervals
+    uint16_t* START = LIST + NP;                                 // [SCAP + 8]
+    __shared__ float s_wa[32], s_wb[32];
+    __shared__ int s_wr[32];
+    __shared__ int s_nslow, s_nhard, s_next;
+    __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
+    if (t == 0) {
+        s_nslow = 0; s_nhard = 0; s_next = 0;
+        s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;
+        s_tab.START = START; s_tab.w = w; s_tab.npts = npts; s_tab.nsg = nsg; s_tab.t0 = t0;
+    }
+
+    // ---- A: depth + image of this thread's CPT source columns -> 8 points in registers
+    const int64_t row_off = ((int64_t)frame * a.h + y) * W;
+    const int c0 = t * CPT, i0 = 1 + 8 * t;
+    float v[8];
     {
-        const uint32_t* img = a.image_u8 + row_off + s0;
-        const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
         float scale;
         const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
         const float* dep = a.depth[eye] + row_off + s0;
-        constexpr int kMaxIter = 4;
-        for (int cbase = 0; cbase < w; cbase += kMaxIter * kPolyThreads) {
-        float dreg[kMaxIter];
-        uint32_t ireg[kMaxIter];
+        const uint32_t* img = a.image_u8 + row_off + s0;
+        float dv[CPT];
+        uint32_t iv[CPT];
+        const bool vec = ((reinterpret_cast<uintptr_t>(dep) | reinterpret_cast<uintptr_t>(img)) & 15) == 0;
+        if (vec && c0 + CPT <= w) {
 #pragma unroll
-        for (int it = 0; it < kMaxIter; ++it) {
-            const int col = cbase + tid + it * kPolyThreads;
-            if (col < w) { dreg[it] = dep[col]; ireg[it] = img[col]; }
+            for (int q = 0; q < CPT / 4; ++q) {
+                const float4 d4 = __ldg(reinterpret_cast<const float4*>(dep + c0) + q);
+                const uint4 i4 = __ldg(reinterpret_cast<const uint4*>(img + c0) + q);
+                dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+                iv[4 * q] = i4.x; iv[4 * q + 1] = i4.y; iv[4 * q + 2] = i4.z; iv[4 * q + 3] = i4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int cc = min(c0 + j, w - 1);   // the column after the last repeats it (padding of IMGP)
+                const bool in = c0 + j <= w;
+                dv[j] = in ? __ldg(dep + cc) : 0.0f;
+                iv[j] = in ? __ldg(img + cc) : 0u;
+            }
         }
+        const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
+        const double base = (double)(c0 + s0) + 0.5;
+        float qv[CPT];
 #pragma unroll
-        for (int it = 0; it < kMaxIter; ++it) {
-            const int col = cbase + tid + it * kPolyThreads;
-            if (col >= w) break;
-            simg[col] = ireg[it];
-            float d = dreg[it];
+        for (int j = 0; j < CPT; ++j) {
+            const bool in = c0 + j < w;
+            float d = dv[j];
             if (scale != 1.0f) d = d * scale;
-            float nd = norm(d);
-            double an = (double)fabsf(nd);
+            const float nd = norm(d);
+            const double an = (double)fabsf(nd);
             double p;
             if (a.expo == 2.0) p = an * an;
             else if (a.expo == 1.0) p = an;
-            else p = pow(an, a.expo);
-            double sp = (nd >= 0.0f) ? p : -p;
-            double cd = sp * div_px;
-            double cx = ((double)(col + s0) + 0.5) + cd;
+            else p = pow_general(an, a.expo);
+            const double sp = (nd >= 0.0f) ? p : -p;
+            const double cd = sp * div_px;
+            double cx = (base + (double)j) + cd;
             cx = cx + sep_px;
-            clo[col + 1] = (float)fabs(cd);
+            qv[j] = in ? (float)fabs(cd) : 0.0f;
             if (SHARP) {
-                px[1 + 2 * col] = (float)(cx - 0.45);
-                px[2 + 2 * col] = (float)(cx + 0.45);
+                v[2 * j] = in ? (float)(cx - 0.45) : INFINITY;
+                v[2 * j + 1] = in ? (float)(cx + 0.45) : INFINITY;
             } else {
-                px[1 + col] = (float)cx;
+                v[j] = in ? (float)cx : INFINITY;
             }
         }
+        const int se = npts - 1 - i0;   // slot of the right sentinel, if it is one of this thread's
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (e == se) v[e] = (float)(2.0 * W);
+        reinterpret_cast<float4*>(X + i0)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(X + i0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int q = 0; q < CPT / 4; ++q) {
+            reinterpret_cast<float4*>(Q + 1 + c0)[q] = make_float4(qv[4 * q], qv[4 * q + 1], qv[4 * q + 2], qv[4 * q + 3]);
+            reinterpret_cast<uint4*>(IMGP + 1 + c0)[q] = make_uint4(iv[4 * q], iv[4 * q + 1], iv[4 * q + 2], iv[4 * q + 3]);
         }
-        if (tid == 0) { px[0] = (float)(-1.0 * W); clo[0] = 0.0f; clo[w + 1] = 0.0f; }
-        for (int i = npts - 1 + tid; i < NP; i += kPolyThreads) px[i] = (i == npts - 1) ? (float)(2.0 * W) : INFINITY;
-        for (int b = tid; b < tw + 4; b += kPolyThreads) start[b] = 0;
+        if (t == 0) { X[0] = (float)(-1.0 * W); Q[0] = 0.0f; IMGP[0] = iv[0]; }
+        // vector path: the pad after the last column (the scalar path loaded it in place)
+        if (c0 + CPT == w && vec) IMGP[1 + w] = iv[CPT - 1];
     }
-    __syncthreads();
 
-    // ---- B: inclusive prefix max / suffix min of px in source order (thread t owns points t*PER .. t*PER+PER-1)
-    float v[PER], lmax[PER], lmin[PER];
-    const int i0 = tid * PER;
+    // ---- B: prefix max / suffix min of x in source order (per-thread totals here, per-point values in C)
+    float em, en;
     {
-#pragma unroll
-        for (int q = 0; q < PER / 4; ++q) {
-            float4 t = reinterpret_cast<const float4*>(px + i0)[q];
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-        float m = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) { m = fmaxf(m, v[e]); lmax[e] = m; }
-        float n = INFINITY;
-#pragma unroll
-        for (int e = PER - 1; e >= 0; --e) { n = fminf(n, v[e]); lmin[e] = n; }
-        // warp-level exclusive scans of the per-thread totals
+        const float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        const float n = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
         float im = m, in_ = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            float t = __shfl_up_sync(0xffffffffu, im, o);
-            if (lane >= o) im = fmaxf(im, t);
-            float u = __shfl_down_sync(0xffffffffu, in_, o);
-            if (lane + o < 32) in_ = fminf(in_, u);
+            const float u = __shfl_up_sync(0xffffffffu, im, o);
+            if (lane >= o) im = fmaxf(im, u);
+            const float d = __shfl_down_sync(0xffffffffu, in_, o);
+            if (lane + o < 32) in_ = fminf(in_, d);
         }
-        if (lane == 31) s_wa[wid] = im;
-        if (lane == 0) s_wb[wid] = in_;
-        float em = __shfl_up_sync(0xffffffffu, im, 1);    // max over earlier lanes of the warp
-        float en = __shfl_down_sync(0xffffffffu, in_, 1); // min over later lanes
+        em = __shfl_up_sync(0xffffffffu, im, 1);     // max over the earlier lanes of the warp
+        en = __shfl_down_sync(0xffffffffu, in_, 1);  // min over the later lanes
         if (lane == 0) em = -INFINITY;
         if (lane == 31) en = INFINITY;
+        if (lane == 31) s_wa[wid] = im;
+        if (lane == 0) s_wb[wid] = in_;
         __syncthreads();
-        for (int q = 0; q < wid; ++q) em = fmaxf(em, s_wa[q]);
-        for (int q = wid + 1; q < kPolyThreads / 32; ++q) en = fminf(en, s_wb[q]);
 #pragma unroll
-        for (int e = 0; e < PER; ++e) { lmax[e] = fmaxf(lmax[e], em); lmin[e] = fminf(lmin[e], en); }
-#pragma unroll
-        for (int q = 0; q < PER / 4; ++q) {
-            reinterpret_cast<float4*>(pm + i0)[q] = make_float4(lmax[4 * q], lmax[4 * q + 1], lmax[4 * q + 2], lmax[4 * q + 3]);
-            reinterpret_cast<float4*>(sm + i0)[q] = make_float4(lmin[4 * q], lmin[4 * q + 1], lmin[4 * q + 2], lmin[4 * q + 3]);
+        for (int q = 0; q < NW; ++q) {
+            if (q < wid) em = fmaxf(em, s_wa[q]);
+            if (q > wid) en = fminf(en, s_wb[q]);
         }
-        // lmax[e] / lmin[e] now hold the INCLUSIVE scans; em / en the exclusive values of the thread's first / last point
-        __syncthreads();
-        // ---- C: stable rank of every point = i - #(earlier, larger) + #(later, smaller).  A point with nothing larger
-        // before it and nothing smaller after it keeps its source index.  The others (folds, jitter) are put on a
-        // work list and counted by the whole CTA, neighbours in a fold going to neighbouring lanes.
-        uint32_t dirty_bits = 0;
+        TMX[t] = fmaxf(em, m);
+        TMN[t] = fminf(en, n);
+    }
+
+    // ---- C: stable rank of every point = i - #(earlier, larger) + #(later, smaller).  Counted over two neighbours on
+    // either side, which is the whole answer when nothing further away is out of order with the point (depth jitter
+    // swaps neighbours); the scans certify that.  Deeper inversions (folds) are counted from shared memory.
+    int r[8];
+    {
+        // P[e] = max of everything before point e, S[e] = min of everything after it
+        float P[8], S[8];
+        P[0] = em;
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
+        for (int e = 1; e < 8; ++e) P[e] = fmaxf(P[e - 1], v[e - 1]);
+        S[7] = en;
+#pragma unroll
+        for (int e = 6; e >= 0; --e) S[e] = fminf(S[e + 1], v[e + 1]);
+        // the neighbouring threads' edge points and what bounds them; across a warp boundary the bounds are the
+        // conservative ones and nothing is counted
+        float pv6 = __shfl_up_sync(0xffffffffu, v[6], 1), pv7 = __shfl_up_sync(0xffffffffu, v[7], 1);
+        float pb6 = __shfl_up_sync(0xffffffffu, P[6], 1), pb7 = __shfl_up_sync(0xffffffffu, P[7], 1);
+        float nv0 = __shfl_down_sync(0xffffffffu, v[0], 1), nv1 = __shfl_down_sync(0xffffffffu, v[1], 1);
+        float na0 = __shfl_down_sync(0xffffffffu, S[0], 1), na1 = __shfl_down_sync(0xffffffffu, S[1], 1);
+        if (lane == 0) { pv6 = -INFINITY; pv7 = -INFINITY; pb6 = em; pb7 = em; }
+        if (lane == 31) { nv0 = INFINITY; nv1 = INFINITY; na0 = en; na1 = en; }
+        uint32_t slow = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
             const float x = v[e];
-            const float pe = (e == 0) ? em : lmax[e - 1];          // max of all earlier points
-            const float se = (e == PER - 1) ? en : lmin[e + 1];    // min of all later points
-            if (!((pe <= x) && (se >= x))) dirty_bits |= 1u << e;
+            const float p1 = (e >= 1) ? v[e >= 1 ? e - 1 : 0] : pv7;
+            const float p2 = (e >= 2) ? v[e >= 2 ? e - 2 : 0] : (e == 1 ? pv7 : pv6);
+            const float b3 = (e >= 2) ? P[e >= 2 ? e - 2 : 0] : (e == 1 ? pb7 : pb6);     // everything before p2
+            const float n1 = (e <= 6) ? v[e <= 6 ? e + 1 : 7] : nv0;
+            const float n2 = (e <= 5) ? v[e <= 5 ? e + 2 : 7] : (e == 6 ? nv0 : nv1);
+            const float a3 = (e <= 5) ? S[e <= 5 ? e + 2 : 7] : (e == 6 ? na0 : na1);     // everything after n2
+            r[e] = i0 + e + ((n1 < x) ? 1 : 0) + ((n2 < x) ? 1 : 0) - ((p1 > x) ? 1 : 0) - ((p2 > x) ? 1 : 0);
+            if (b3 > x || a3 < x) slow |= 1u << e;
         }
-        if (dirty_bits) {
-            int base = atomicAdd(&s_ndirty, __popc(dirty_bits));
+        *reinterpret_cast<uint4*>(RNK + i0) = make_uint4((uint32_t)r[0] | ((uint32_t)r[1] << 16), (uint32_t)r[2] | ((uint32_t)r[3] << 16),
+                                                         (uint32_t)r[4] | ((uint32_t)r[5] << 16), (uint32_t)r[6] | ((uint32_t)r[7] << 16));
+        if (slow) {
+            int base = atomicAdd(&s_nslow, __popc(slow));
 #pragma unroll
-            for (int e = 0; e < PER; ++e)
-                if (dirty_bits & (1u << e)) dlist[base++] = (unsigned short)(i0 + e);
+            for (int e = 0; e < 8; ++e)
+                if (slow & (1u << e)) LIST[base++] = (uint16_t)(i0 + e);
         }
         __syncthreads();
-        const int ndirty = s_ndirty;
-        for (int q = tid; q < ndirty; q += kPolyThreads) {
-            const int i = dlist[q];
-            const float x = px[i];
-            int r = i;
-            for (int j = i - 1; j >= 0 && pm[j] > x; --j) r -= (px[j] > x) ? 1 : 0;
-            for (int j = i + 1; j < npts && sm[j] < x; ++j) r += (px[j] < x) ? 1 : 0;
-            drank[i] = (unsigned short)r;
-        }
-        __syncthreads();   // pm / sm are dead from here on: sxd overwrites them
+        const int nslow = s_nslow;
+        if (nslow) {
+            // thread blocks of 8 points outwards from the point's own; a block is skipped, and the walk ends, as soon as
+            // its running bound says that nothing at or beyond it can be out of order with x
+            for (int q = t; q < nslow; q += NT) {
+                const int i = LIST[q];
+                const float x = X[i];
+                const int tb0 = (i - 1) >> 3;
+                int rr = i;
+                for (int tb = tb0; tb >= 0; --tb) {
+                    if (tb != tb0 && !(TMX[tb] > x)) break;
+                    const float4 u0 = reinterpret_cast<const float4*>(X + 1 + 8 * tb)[0], u1 = reinterpret_cast<const float4*>(X + 1 + 8 * tb)[1];
+                    const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    const int lim = (tb == tb0) ? (i - 1) - 8 * tb : 8;   // own block: only the points before i
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
+                    for (int e = 0; e < 8; ++e) rr -= (e < lim && u[e] > x) ? 1 : 0;
+                }
+                for (int tb = tb0; tb < NT; ++tb) {
+                    if (tb != tb0 && !(TMN[tb] < x)) break;
+                    const float4 u0 = reinterpret_cast<const float4*>(X + 1 + 8 * tb)[0], u1 = reinterpret_cast<const float4*>(X + 1 + 8 * tb)[1];
+                    const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    const int lim = (tb == tb0) ? (i - 1) - 8 * tb : -1;  // own block: only the points after i
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) rr += (e > lim && u[e] < x) ? 1 : 0;
+                }
+                RNK[i] = (uint16_t)rr;
+            }
+            __syncthreads();
+            const uint4 pk = *reinterpret_cast<const uint4*>(RNK + i0);
+            r[0] = pk.x & 0xFFFF; r[1] = pk.x >> 16; r[2] = pk.y & 0xFFFF; r[3] = pk.y >> 16;
+            r[4] = pk.z & 0xFFFF; r[5] = pk.z >> 16; r[6] = pk.w & 0xFFFF; r[7] = pk.w >> 16;
+        }
+        const int rn = RNK[i0 + 8];   // rank of the next thread's first point
+        uint16_t* END16 = reinterpret_cast<uint16_t*>(ER);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
             const int i = i0 + e;
             if (i < npts) {
-                const int r = (dirty_bits & (1u << e)) ? (int)drank[i] : i;
-                sxd[r] = (double)v[e];
-                sidx[r] = (unsigned short)i;
+                const int k = r[e];
+                SX[k] = v[e];
+                SID[k] = (uint16_t)i;
+                END16[2 * k] = (uint16_t)((i < npts - 1) ? (e < 7 ? r[e < 7 ? e + 1 : 7] : rn) : 0);
             }
         }
+        if (t == 0) { SX[0] = (float)(-1.0 * W); SID[0] = 0; END16[0] = (uint16_t)r[0]; }
     }
     __syncthreads();
 
-    // ---- D: reach = prefix max over sorted segments of their end x1; bucket starts
+    // ---- D: REACH = prefix max of END in sorted order; bucket starts; intervals with a single candidate
     {
-        float m = -INFINITY;
-        float loc[PER], avv[PER], x1v[PER];
-        int spv[PER];
-        int bprev;
+        const int k0 = 8 * t;
+        uint32_t er[8], sid[8];
+        float sx[8];
         {
-            int kp = i0 - 1;
-            if (kp < 0) bprev = -1;
-            else if (kp >= npts) bprev = tw + 1;
-            else bprev = min(max(__float2int_rd(px[sidx[kp]]) - t0 + 1, 0), tw + 1);
+            const uint4 a0 = reinterpret_cast<const uint4*>(ER + k0)[0], a1 = reinterpret_cast<const uint4*>(ER + k0)[1];
+            er[0] = a0.x; er[1] = a0.y; er[2] = a0.z; er[3] = a0.w; er[4] = a1.x; er[5] = a1.y; er[6] = a1.z; er[7] = a1.w;
+            const float4 b0 = reinterpret_cast<const float4*>(SX + k0)[0], b1 = reinterpret_cast<const float4*>(SX + k0)[1];
+            sx[0] = b0.x; sx[1] = b0.y; sx[2] = b0.z; sx[3] = b0.w; sx[4] = b1.x; sx[5] = b1.y; sx[6] = b1.z; sx[7] = b1.w;
+            const uint4 c4 = *reinterpret_cast<const uint4*>(SID + k0);
+            sid[0] = c4.x & 0xFFFF; sid[1] = c4.x >> 16; sid[2] = c4.y & 0xFFFF; sid[3] = c4.y >> 16;
+            sid[4] = c4.z & 0xFFFF; sid[5] = c4.z >> 16; sid[6] = c4.w & 0xFFFF; sid[7] = c4.w >> 16;
         }
+        const float sxp = (t > 0) ? SX[k0 - 1] : 0.0f;
+        int end[8], lr[8];
+        int m = 0;
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int k = i0 + e;
-            float x1 = -INFINITY;
-            avv[e] = 0.0f; spv[e] = 0;
-            if (k < npts) {
-                const int sp = (int)sidx[k];
-                if (k < nsg) x1 = px[sp + 1];
-                const float pv = px[sp];
-                avv[e] = pv; spv[e] = sp;
-                // bucket = floor(x) - t0 + 1 clamped to [0, tw + 1] (the float -> int conversion saturates)
-                const int b = min(max(__float2int_rd(pv) - t0 + 1, 0), tw + 1);
-                if (b > bprev) {
-                    start[b] = k;
-                    for (int q = bprev + 1; q < b; ++q) start[q] = k;   // empty buckets in between (holes)
-                    bprev = b;
-                }
-                if (k == npts - 1) start[tw + 2] = npts;
-            }
-            x1v[e] = x1;
-            m = fmaxf(m, x1);
-            loc[e] = m;
+        for (int e = 0; e < 8; ++e) {
+            end[e] = (k0 + e < npts) ? (int)(er[e] & 0xFFFFu) : 0;
+            m = max(m, end[e]);
+            lr[e] = m;
         }
-        float im = m;
+        int im = m;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            float t = __shfl_up_sync(0xffffffffu, im, o);
-            if (lane >= o) im = fmaxf(im, t);
+            const int u = __shfl_up_sync(0xffffffffu, im, o);
+            if (lane >= o) im = max(im, u);
         }
-        if (lane == 31) s_wa[wid] = im;
-        float em = __shfl_up_sync(0xffffffffu, im, 1);
-        if (lane == 0) em = -INFINITY;
+        int emr = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane == 0) emr = 0;
+        if (lane == 31) s_wr[wid] = im;
         __syncthreads();
-        for (int q = 0; q < wid; ++q) em = fmaxf(em, s_wa[q]);
 #pragma unroll
-        for (int q = 0; q < PER / 4; ++q)
-            reinterpret_cast<float4*>(reach + i0)[q] = make_float4(fmaxf(loc[4 * q], em), fmaxf(loc[4 * q + 1], em),
-                                                                   fmaxf(loc[4 * q + 2], em), fmaxf(loc[4 * q + 3], em));
-        // ---- D2 (first half): an interval whose left point no EARLIER segment reaches past has exactly its own
-        // segment as candidate (or none, if that one does not go forward).  Everything else goes to a work list.
+        for (int q = 0; q < NW; ++q)
+            if (q < wid) emr = max(emr, s_wr[q]);
+        uint32_t wsp[8];
         uint32_t hard = 0;
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int k = i0 + e;
-            if (k >= nsg) continue;
-            const float rprev = (e == 0) ? em : fmaxf(loc[e - 1], em);   // reach[k - 1]
-            if (rprev > avv[e]) {
-                hard |= 1u << e;
-            } else {
-                const uint32_t code = (x1v[e] > avv[e]) ? 1u : 0u;
-                cand[k] = (unsigned short)code;
-            }
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            const int rprev = (e == 0) ? emr : max(emr, lr[e > 0 ? e - 1 : 0]);   // REACH[k - 1]
+            er[e] = (uint32_t)end[e] | ((uint32_t)max(emr, lr[e]) << 16);
+            // nobody reaches past this interval's left point: its own segment wins, if that one goes forward
+            wsp[e] = sid[e] | ((end[e] > k) ? 0u : poly::kUnresolved);
+            if (k < nsg && rprev > k) hard |= 1u << e;
         }
+        reinterpret_cast<uint4*>(ER + k0)[0] = make_uint4(er[0], er[1], er[2], er[3]);
+        reinterpret_cast<uint4*>(ER + k0)[1] = make_uint4(er[4], er[5], er[6], er[7]);
+        *reinterpret_cast<uint4*>(WSP + k0) = make_uint4(wsp[0] | (wsp[1] << 16), wsp[2] | (wsp[3] << 16),
+                                                         wsp[4] | (wsp[5] << 16), wsp[6] | (wsp[7] << 16));
         if (hard) {
-            int base = atomicAdd(&s_ntwo, __popc(hard));
+            int base = atomicAdd(&s_nhard, __popc(hard));
 #pragma unroll
-            for (int e = 0; e < PER; ++e)
-                if (hard & (1u << e)) tlist[base++] = (unsigned short)(i0 + e);
+            for (int e = 0; e < 8; ++e)
+                if (hard & (1u << e)) LIST[base++] = (uint16_t)(k0 + e);
         }
+        // bucket b = floor(x) - t0 + 1 clamped to [0, tw + 1] (the float -> int conversion saturates)
+        int bprev = -1;
+        if (t > 0) bprev = (k0 - 1 < npts) ? min(max(__float2int_rd(sxp) - t0 + 1, 0), tw + 1) : tw + 1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            const int b = (k < npts) ? min(max(__float2int_rd(sx[e]) - t0 + 1, 0), tw + 1) : bprev;
+            if (b != bprev) {
+                START[b] = (uint16_t)k;
+                if (b > bprev + 1)                                              // empty buckets in between (gaps)
+                    for (int q = bprev + 1; q < b; ++q) START[q] = (uint16_t)k;
+                bprev = b;
+            }
+        }
+        if (k0 <= npts - 1 && npts - 1 < k0 + 8) START[tw + 2] = (uint16_t)npts;
     }
     __syncthreads();
 
-    // ---- D2 (second half): active set of the listed intervals (a, b) = (point k, point k+1).  For a centre strictly
-    // inside, a segment j is active iff it starts at or before a (j <= k) and ends beyond a; nothing between a and b
-    // is a point, so all of this is float32 comparisons.  Up to two active segments are encoded in cand[k].
+    Tab tab;   // register copy for the inlined float32 path
+    tab.X = X; tab.SX = SX; tab.ER = ER; tab.SID = SID; tab.WSP = WSP; tab.Q = Q; tab.IMGP = IMGP; tab.START = START;
+    tab.w = w; tab.npts = npts; tab.nsg = nsg; tab.t0 = t0;
     {
-        const int nlist = s_ntwo;
-        for (int q = tid; q < nlist; q += kPolyThreads) {
-            const int k = tlist[q];
-            const uint32_t me = sidx[k];
-            const float av = px[me];
-            int cnt = 0, o1 = 0, o2 = 0;
-            for (int j = k; j >= 0 && reach[j] > av; --j) {
-                const int sp = (int)sidx[j];
-                if (px[sp + 1] > av) {
-                    if (cnt == 0) o1 = k - j; else if (cnt == 1) o2 = k - j;
-                    ++cnt;
-                }
-            }
-            uint32_t code = (uint32_t)min(cnt, 3);
-            if (o1 > 127 || o2 > 127) code = 3u;
-            if (code == 2u) {
-                // Interpolated closeness is linear in the centre, so if one candidate leads at both ends of the interval
-                // by more than any rounding could matter, it leads at every centre inside: the interval becomes a
-                // one-candidate interval.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
-                // segment, and ip < 1 can only fail (float32 rounding of x1 - x0) for long segments that end at or just
-                // beyond this interval's right point -- those stay two-candidate and are decided per visit in FP64.
-                const float bv = px[sidx[k + 1]];
-                const int spA = (int)sidx[k - o1], spB = (int)sidx[k - o2];
-                const float ax0 = px[spA], ax1 = px[spA + 1], bx0 = px[spB], bx1 = px[spB + 1];
-                const float aq0 = clo[pt_slot(spA, SHARP)], aq1 = clo[pt_slot(spA + 1, SHARP)];
-                const float bq0 = clo[pt_slot(spB, SHARP)], bq1 = clo[pt_slot(spB + 1, SHARP)];
-                const float ad = ax1 - ax0, bd = bx1 - bx0;
-                // ip < 1 is guaranteed when the centre stays more than half a float32 ulp of (x1 - x0) below x1:
-                // always for lengths < 2 (the centre is >= 1e-7 below the interval's end), else when x1 is far enough
-                // beyond the interval
-                const bool safe = (ad < 2.0f || (ax1 - bv) > ad * 1.2e-7f) && (bd < 2.0f || (bx1 - bv) > bd * 1.2e-7f);
-                // closeness of both candidates at the two ends (float32 is plenty: the margin below is 1e-3)
-                const float ta = __fdividef(av - ax0, ad), tb = __fdividef(bv - ax0, ad);
-                const float ua = __fdividef(av - bx0, bd), ub = __fdividef(bv - bx0, bd);
-                const float a_lo = aq0 + ta * (aq1 - aq0), a_hi = aq0 + tb * (aq1 - aq0);
-                const float b_lo = bq0 + ua * (bq1 - bq0), b_hi = bq0 + ub * (bq1 - bq0);
-                const float margin = 1e-3f + 1e-4f * fmaxf(fmaxf(aq0, aq1), fmaxf(bq0, bq1));
-                if (safe && a_lo > b_lo + margin && a_hi > b_hi + margin) code = 1u;                     // first candidate
-                else if (safe && b_lo > a_lo + margin && b_hi > a_hi + margin) { code = 1u; o1 = o2; }  // second candidate
-            }
-            cand[k] = (unsigned short)(code | ((uint32_t)(o1 & 127) << kOff1Shift) | ((uint32_t)(o2 & 127) << kOff2Shift));
+        const int nhard = s_nhard;
+        for (int q = t; q < nhard; q += NT) {
+            const int k = LIST[q];
+            WSP[k] = (uint16_t)poly::classify_interval<SHARP>(tab, k);
         }
     }
     __syncthreads();
 
-    // ---- E: sweep, one thread per output column
-    PolyCtx ctx;
-    ctx.px = px; ctx.sxd = sxd; ctx.sidx = sidx; ctx.reach = reach; ctx.clo = clo; ctx.start = start; ctx.row = c;
-    ctx.t0 = t0;
+    // ---- E: sweep.  Warps take 32-column blocks from a shared counter (blocks inside folds cost several times more).
     uint32_t* out = a.out[eye] + row_off + t0;
-    bool give_up = false;
-    constexpr bool shp = SHARP;
-    // warps take 32-column blocks from a shared counter: blocks inside folds cost several times more than smooth ones
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
+    const bool all_exact = (mode_flags & 8) != 0;
+    bool give_up = false;
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(&s_next, 1);
         blk = __shfl_sync(0xffffffffu, blk, 0);
         if (blk >= nblk) break;
-        const int col = first + (blk << 5) + lane;     // output column relative to the bucket origin t0
+        const int col = first + (blk << 5) + lane;
         if (col >= tw) continue;
-        double c0 = 0.5, c1 = 0.5, c2 = 0.5;   // float32-valued accumulators kept in float64 registers
-        const int k0 = start[col + 1] - 1, k1 = start[col + 2] - 1;
-        const double cold = u8_to_f64((uint32_t)(col + t0)), col1d = cold + 1.0;
-        double pa = sxd[k0];
-        for (int k = k0; k <= k1; ++k) {
-            const double pb = sxd[k + 1];
-            const double from = ((pa > cold) ? pa : cold) + kEps;     // no NaNs here: plain compare-select
-            const double to = ((pb < col1d) ? pb : col1d) - kEps;
-            const double sig = to - from;
-            const double ctr = from + 0.5 * sig;
-            const uint32_t inf = cand[k];
-            const uint32_t code = inf & 3u;
-            int sp;
-            bool resolved = false, off_is_k = false;
-            if (code == 1u && sig > 0.0) {
-                const int off1 = (int)((inf >> kOff1Shift) & 127u);
-                sp = (int)sidx[k - off1];
-                off_is_k = (off1 == 0);   // the segment starts at this interval's left point: x0 = pa
-                resolved = true;
-            }
-            if (!resolved) {
-                off_is_k = false;
-                sp = general_visit(ctx, col, k, ctr);
-                if (sp == -2) { give_up = true; sp = -1; }
-                if (sp < 0) { pa = pb; continue; }
-            }
-            const int sl = pt_slot(sp, shp), sr = pt_slot(sp + 1, shp);
-            const int cl = slot_col(sl, w), cr = slot_col(sr, w);
-            const uint32_t pl = simg[cl];
-            double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
-            if (cl != cr) {
-                // ip = (ctr - x0) / (x1 - x0) with the reference's float32 subtraction in the denominator
-                const double x0 = off_is_k ? pa : (double)px[sp];
-                const double x1 = (double)px[sp + 1];
-                const double den = round24_even(x1 - x0);
-                const double ip = (ctr - x0) / den;
-                const uint32_t pr = simg[cr];
-                const double om = 1.0 - ip;
-                double t0 = v0 * om, t1 = u8_to_f64(pr & 255u) * ip;
-                v0 = t0 + t1;
-                t0 = v1 * om; t1 = u8_to_f64((pr >> 8) & 255u) * ip;
-                v1 = t0 + t1;
-                t0 = v2 * om; t1 = u8_to_f64((pr >> 16) & 255u) * ip;
-                v2 = t0 + t1;
-            }
-            c0 = round24_fp(c0 + v0 * sig);
-            c1 = round24_fp(c1 + v1 * sig);
-            c2 = round24_fp(c2 + v2 * sig);
-            pa = pb;
+        uint32_t px = 0;
+        const bool ok = poly::fast_column<SHARP>(tab, col, &px) && !all_exact;
+        if (!ok) {
+            px = poly::exact_column<SHARP>(s_tab, col);
+            if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
         }
-        out[col] = pack_rgbx(__double2int_rz(c0), __double2int_rz(c1), __double2int_rz(c2));
+        out[col] = px;
     }
-    if (give_up) s_flag = 1;
-    __syncthreads();
-    const int flagged = s_flag;
-    if (tid == 0 && tile_w > 0) {
-        // a tile cannot replay the whole row: flag it for k_polylines_exact, which runs right after this kernel
-        if (flagged) atomicOr(&row_flags[((int64_t)frame * 2 + eye) * a.h + y], 1);
-    } else if (tid == 0) {
-        if (row_flags) row_flags[((int64_t)frame * 2 + eye) * a.h + y] = flagged;
-        if (flagged) {
-            // the list replay did not fit its budget somewhere in this row: redo the row sequentially
-            // (reach[] is dead now and serves as the active list)
-            bool ovf = sequential_row(ctx, simg, out, reinterpret_cast<unsigned short*>(reach), 2 * NP);
-            if (ovf) atomicOr(status, 1);
-        }
+    if (give_up) {
+        // a list replay did not fit its budget (or its history starts left of this tile): the row is redone sequentially
+        const int rowid = (frame * 2 + eye) * a.h + y;
+        if (atomicOr(&row_flags[rowid], 1) == 0) row_list[atomicAdd(&counters[1], 1)] = rowid;
     }
-}
-
-template <int PER>
-static size_t fast_smem_per(int w) {
-    return (size_t)kPolyThreads * PER * (4 + 8 + 4 + 4 + 2) + (size_t)(w + 4) * 4 + (size_t)(w + 4) * 4 + (size_t)w * 4;
 }
 
 static size_t exact_smem(int w, int sharp, int act_cap) {
@@ -879,28 +646,10 @@ static size_t exact_smem(int w, int sharp, int act_cap) {
     size_t np2 = npts + (npts & 1);
     return npts * 4 + (size_t)w * 4 + (size_t)(w + 4) * 4 + np2 * 2 * 3 + (size_t)act_cap * 2;
 }
-size_t polylines_scratch_bytes(int n, int h) { return ((size_t)n * 2 * h + 16) * sizeof(int); }
+// scratch: [16] counters (0: status bits, 1: listed rows) + [n*2*h] row flags + [n*2*h] row list
+size_t polylines_scratch_bytes(int n, int h) { return ((size_t)n * 2 * h * 2 + 16) * sizeof(int); }
 
-template <int PER>
-static cudaError_t launch_fast(const WarpArgs& a, int sharp, int* flags, int* status, int wmax, int tile_w, int tile_ext,
-                               int ntiles, double reach0, double reach1, cudaStream_t s) {
-    const size_t fs = fast_smem_per<PER>(wmax);
-    const void* fn = tile_w > 0 ? (sharp ? (const void*)k_polylines<PER, true, true> : (const void*)k_polylines<PER, false, true>)
-                                : (sharp ? (const void*)k_polylines<PER, true, false> : (const void*)k_polylines<PER, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs);
-    if (e != cudaSuccess) return e;
-    prof_begin(K_POLY_FAST, s);
-    const dim3 grid(a.h, a.n, 2 * ntiles);
-#define CS_POLY_LAUNCH(SH, TL) k_polylines<PER, SH, TL><<<grid, kPolyThreads, fs, s>>>(a, flags, status, tile_w, tile_ext, reach0, reach1)
-    if (tile_w > 0) { if (sharp) CS_POLY_LAUNCH(true, true); else CS_POLY_LAUNCH(false, true); }
-    else { if (sharp) CS_POLY_LAUNCH(true, false); else CS_POLY_LAUNCH(false, false); }
-#undef CS_POLY_LAUNCH
-    prof_end(K_POLY_FAST, s);
-    count_launch();
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_exact(const WarpArgs& a, int sharp, const int* flags, int* status, cudaStream_t s) {
+static cudaError_t launch_exact(const WarpArgs& a, int sharp, bool listed, int* counters, int* list, cudaStream_t s) {
     const size_t kMaxSmem = 227 * 1024;
     double dmax = fmax(fabs(a.eye[0].div_px), fabs(a.eye[1].div_px));
     long long cap_ref = 5ll * (long long)dmax + 25;    // the reference's own list capacity, SIG:1947
@@ -910,53 +659,127 @@ static cudaError_t launch_exact(const WarpArgs& a, int sharp, const int* flags, 
     int act_cap = (int)(cap_ref < cap_fit ? cap_ref : cap_fit);
     size_t es = exact_smem(a.w, sharp, act_cap);
     if (es > 48 * 1024) cudaFuncSetAttribute(k_polylines_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
+    const int rows = a.n * 2 * a.h;
+    // listed rows are rare (usually none): a small grid that strides over the list
+    const int grid = listed ? (rows < 296 ? rows : 296) : rows;
     prof_begin(K_POLY_EXACT, s);
-    k_polylines_exact<<<dim3(a.h, a.n, 2), kPolyThreads, es, s>>>(a, sharp, act_cap, flags, status);
+    k_polylines_exact<<<grid, kExactThreads, es, s>>>(a, sharp, act_cap, listed ? list : nullptr, counters + 1, counters);
     prof_end(K_POLY_EXACT, s);
     count_launch();
     return cudaGetLastError();
 }
 
-// scratch: [n*2*h] row flags + [1] status word.
-// flags bit 0 = replay every row with the sequential kernel, bit 2 = force 64-column tiles (tests).
-cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s) {
-    const int sharp = a.fill == CS_FILL_POLYLINES_SHARP;
-    const int w = a.w;
-    if (a.scratch_bytes < polylines_scratch_bytes(a.n, a.h)) return cudaErrorInvalidValue;
-    const int npts = (sharp ? 2 * w : w) + 2;
-    if (npts > 65535) return cudaErrorInvalidValue;
-    int* flags = reinterpret_cast<int*>(a.scratch);
-    int* status = flags + (size_t)a.n * 2 * a.h;
-    const size_t kMaxSmem = 227 * 1024;
-    const bool force_exact = (a.flags & 1) != 0, force_tiles = (a.flags & 4) != 0;
-    if (!force_exact) {
-        // whole row per CTA while two CTAs still fit on an SM
-        if (!force_tiles) {
-            if (npts <= kPolyThreads * 4 && fast_smem_per<4>(w) <= kMaxSmem) return launch_fast<4>(a, sharp, flags, status, w, 0, 0, 1, 0.0, 0.0, s);
-            if (npts <= kPolyThreads * 8 && fast_smem_per<8>(w) <= kMaxSmem) return launch_fast<8>(a, sharp, flags, status, w, 0, 0, 1, 0.0, 0.0, s);
+struct PolyPlan {
+    int nw;
+    PolyGeom g;
+    int max_tiles;
+    double cost;
+};
+
+// Tile geometry for CTAs of nw warps; false when no useful tile fits.  cost ~ relative work per output column.
+static bool plan_for(int nw, const WarpArgs& a, bool sharp, bool force_tiles, PolyPlan* p) {
+    const int ppc = sharp ? 2 : 1;
+    const int np = nw * 256, cap_cols = (np - 2) / ppc - 4;
+    const double span = pow(fmax((double)a.conv, 1.0 - (double)a.conv), a.expo);
+    p->nw = nw; p->max_tiles = 0; p->cost = 0.0;
+    for (int eye = 0; eye < 2; ++eye) {
+        p->g.tile_w[eye] = a.w; p->g.ext[eye] = 0; p->g.ntiles[eye] = 0; p->g.lo_off[eye] = 0; p->g.hi_off[eye] = 0;
+        if (a.eye[eye].passthrough) continue;
+        // |shift| <= |div_px| * max(conv, 1 - conv)^expo because the normalised depth lies in [-conv, 1 - conv]
+        const double reach = fabs(a.eye[eye].div_px) * span + 1.0;
+        if (reach + fabs(a.eye[eye].sep_px) > 1e6) return false;
+        // a source column c lands within reach + 1 of c + sep: the window of bucket columns [t0, t0 + tw)
+        p->g.lo_off[eye] = (int)floor(-a.eye[eye].sep_px - (reach + 4.0));
+        p->g.hi_off[eye] = (int)ceil(-a.eye[eye].sep_px + (reach + 4.0));
+        if (!force_tiles && a.w <= cap_cols) {
+            p->g.ntiles[eye] = 1;
+            p->cost += 0.45 + 0.55 * (double)(np / ppc) / a.w;
+        } else {
+            const int rmax = (int)ceil(reach);
+            const int ext = 2 * rmax + 8;                       // a fold is at most 2 * reach wide
+            const int guard = 2 * (rmax + 5) + 2 + ext + 4;
+            int tile_w = force_tiles ? 64 : ((cap_cols - guard) / 32) * 32;
+            if (tile_w < 64 || tile_w + guard > cap_cols) return false;
+            int ntiles = (a.w + tile_w - 1) / tile_w;
+            if (!force_tiles) tile_w = (((a.w + ntiles - 1) / ntiles + 31) / 32) * 32;   // even tiles
+            ntiles = (a.w + tile_w - 1) / tile_w;
+            p->g.tile_w[eye] = tile_w; p->g.ext[eye] = ext; p->g.ntiles[eye] = ntiles;
+            p->cost += 0.45 + 0.55 * (double)(np / ppc) * ntiles / a.w;
         }
-        // wider rows: tiles of output columns, each with the source window that can reach it.  |shift| is bounded by
-        // |div_px| * max(conv, 1 - conv)^expo because the normalised depth lies in [-conv, 1 - conv].
-        const double span = pow(fmax((double)a.conv, 1.0 - (double)a.conv), a.expo);
-        const double reach0 = fabs(a.eye[0].div_px) * span + 1.0, reach1 = fabs(a.eye[1].div_px) * span + 1.0;
-        const int rmax = (int)ceil(fmax(reach0, reach1));
-        const int tile_ext = 2 * rmax + 8;                      // a fold is at most 2 * reach wide
-        const int guard = 2 * (rmax + 5) + 2 + tile_ext;
-        const int cap_cols = force_tiles ? (kPolyThreads * 4 - 2) / (sharp ? 2 : 1) : (kPolyThreads * 8 - 2) / (sharp ? 2 : 1);
-        int tile_w = force_tiles ? 64 : ((cap_cols - guard) / 32) * 32;
-        if (tile_w >= 64 && tile_w + guard <= cap_cols) {
-            const int wmax = (tile_w + guard < w) ? tile_w + guard : w;
-            const int ntiles = (w + tile_w - 1) / tile_w;
-            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)a.n * 2 * a.h * sizeof(int), s);
+        if (p->g.ntiles[eye] > p->max_tiles) p->max_tiles = p->g.ntiles[eye];
+    }
+    return p->max_tiles > 0;
+}
+
+template <int NW, bool SHARP, int TPS>
+static cudaError_t launch_tiles_occ(const WarpArgs& a, const PolyPlan& p, int* counters, int* flags, int* list, cudaStream_t s) {
+    using L = PolyLayout<NW, SHARP>;
+    static bool attr_done = false;   // benign race: the attribute is idempotent
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_polylines<NW, SHARP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    prof_begin(K_POLY_FAST, s);
+    k_polylines<NW, SHARP, TPS><<<dim3(p.max_tiles, a.h, 2 * a.n), NW * 32, L::kBytes, s>>>(a, p.g, flags, list, counters, a.flags);
+    prof_end(K_POLY_FAST, s);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int NW, bool SHARP>
+static cudaError_t launch_tiles(const WarpArgs& a, const PolyPlan& p, int* counters, int* flags, int* list, cudaStream_t s) {
+    static int occ = -1;
+    if (occ < 0) { const char* v = getenv("COMFYSTEREO_POLY_OCC"); occ = v ? atoi(v) : 0; }
+    if (occ == 1) return launch_tiles_occ<NW, SHARP, 768>(a, p, counters, flags, list, s);
+    if (occ == 2) return launch_tiles_occ<NW, SHARP, 512>(a, p, counters, flags, list, s);
+    return launch_tiles_occ<NW, SHARP, 1024>(a, p, counters, flags, list, s);
+}
+
+// flags bit 0 = replay every row with the sequential kernel, bit 2 = force 64-column tiles, bit 3 = every column through
+// exact_column (tests); bits 8-15 = CTA size in warps (0 = choose)
+cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s) {
+    const bool sharp = a.fill == CS_FILL_POLYLINES_SHARP;
+    if (a.scratch_bytes < polylines_scratch_bytes(a.n, a.h)) return cudaErrorInvalidValue;
+    if ((sharp ? 2 * (long long)a.w : (long long)a.w) + 2 > 65535) return cudaErrorInvalidValue;
+    int* counters = reinterpret_cast<int*>(a.scratch);
+    int* flags = counters + 16;
+    int* list = flags + (size_t)a.n * 2 * a.h;
+    cudaError_t e = cudaMemsetAsync(counters, 0, (16 + (size_t)a.n * 2 * a.h) * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const bool force_exact = (a.flags & 1) != 0, force_tiles = (a.flags & 4) != 0;
+    int want_nw = (a.flags >> 8) & 0xFF;
+    if (!want_nw) {
+        static int env_nw = -1;
+        if (env_nw < 0) { const char* v = getenv("COMFYSTEREO_POLY_NW"); env_nw = v ? atoi(v) : 0; }
+        want_nw = env_nw;
+    }
+    if (!force_exact) {
+        static const int kSizes[] = {4, 8, 16};
+        PolyPlan best;
+        bool have = false;
+        for (int nw : kSizes) {
+            if (want_nw && nw != want_nw) continue;
+            PolyPlan p;
+            if (!plan_for(nw, a, sharp, force_tiles, &p)) continue;
+            if (force_tiles) { best = p; have = true; break; }
+            if (!have || p.cost < best.cost - 1e-9) { best = p; have = true; }
+        }
+        if (have) {
+#define CS_POLY_CASE(NWV) case NWV: e = sharp ? launch_tiles<NWV, true>(a, best, counters, flags, list, s) \
+                                              : launch_tiles<NWV, false>(a, best, counters, flags, list, s); break;
+            switch (best.nw) {
+                CS_POLY_CASE(4)
+                CS_POLY_CASE(8)
+                CS_POLY_CASE(16)
+                default: e = cudaErrorInvalidValue;
+            }
+#undef CS_POLY_CASE
             if (e != cudaSuccess) return e;
-            e = force_tiles ? launch_fast<4>(a, sharp, flags, status, wmax, tile_w, tile_ext, ntiles, reach0, reach1, s)
-                            : launch_fast<8>(a, sharp, flags, status, wmax, tile_w, tile_ext, ntiles, reach0, reach1, s);
-            if (e != cudaSuccess) return e;
-            return launch_exact(a, sharp, flags, status, s);   // rows a tile could not finish (usually none)
+            return launch_exact(a, sharp, true, counters, list, s);   // rows a tile could not finish (usually none)
         }
     }
     // the test hook, or a disparity range so large that no useful tile fits: sequential kernel for every row
-    return launch_exact(a, sharp, nullptr, status, s);
+    return launch_exact(a, sharp, false, counters, list, s);
 }
 
 }  // namespace cs

@@ -95,6 +95,15 @@ def test_warp_stage(gu, spec):
         # and so must the tiled variant used for rows too wide for one CTA (forced here: 64-column tiles)
         tl = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"], flags=4)
         assert np.array_equal(tl[..., :3], g["out"])
+        # every column through the FP64 exact_column path (flag 8) instead of the certified float32 path
+        ec = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"], flags=8)
+        assert np.array_equal(ec[..., :3], g["out"])
+        # every CTA size (bits 8-15 = warps per CTA), whole rows or natural tiles, and forced 64-column tiles
+        for nw in (4, 8, 16):
+            for fl in (0, 4):
+                o = gu.warp_fill(probe, d255, spec["fill"], spec["div"], spec["sep"], spec["expo"], spec["conv"],
+                                 flags=(nw << 8) | fl)
+                assert np.array_equal(o[..., :3], g["out"]), (nw, fl)
 
 
 @pytest.mark.parametrize("spec", STAGE["gpuwarp"], ids=[s["name"] + "_" + s["kind"] for s in STAGE["gpuwarp"]])
