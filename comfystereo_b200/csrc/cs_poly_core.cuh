@@ -259,6 +259,78 @@ CS_HDN uint32_t exact_column(const Tab& c, int col) {
     return pack3((int)c0, (int)c1, (int)c2) | (ok ? 0u : kGaveUp);
 }
 
+#ifdef __CUDACC__
+// exact_column by a whole warp: all 32 lanes call it with the same column.  The sub-intervals of a column are independent
+// up to the colour accumulation (centre, winner, interpolation parameter, the three products colour * significance), so
+// each lane prepares one sub-interval; only the float32-rounded running sums are then formed in order.  Same operations
+// in the same order as exact_column, a third of its latency -- the CTA waits for these columns with everything else done.
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src), hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
+    return __hiloint2double(hi, lo);
+}
+template <bool SHARP>
+__device__ __noinline__ uint32_t exact_column_warp(const Tab& c, int col) {
+    const int lane = threadIdx.x & 31;
+    double c0 = 0.5, c1 = 0.5, c2 = 0.5;
+    const int k0 = (int)c.START[col + 1] - 1, k1 = (int)c.START[col + 2] - 1;
+    const double cold = (double)(col + c.t0), col1d = cold + 1.0;
+    bool ok = true;
+    for (int kb = k0; kb <= k1; kb += 32) {
+        const int k = kb + lane;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        bool have = false, bad = false;
+        if (k <= k1) {
+            const double pa = (double)c.SX[k], pb = (double)c.SX[k + 1];
+            const double from = ((pa > cold) ? pa : cold) + kEps;
+            const double to = ((pb < col1d) ? pb : col1d) - kEps;
+            const double sig = to - from;
+            const double ctr = from + 0.5 * sig;
+            const uint32_t inf = c.WSP[k];
+            int sp;
+            if (!(inf & kUnresolved) && sig > 0.0) {
+                sp = (int)inf;
+            } else {
+                sp = general_visit<SHARP>(c, col, k, ctr);
+                if (sp == -2) { bad = true; sp = -1; }
+            }
+            if (sp >= 0) {
+                const int cl = slot_col(pt_slot<SHARP>(sp), c.w), cr = slot_col(pt_slot<SHARP>(sp + 1), c.w);
+                const uint32_t pl = c.IMGP[cl + 1];
+                double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
+                if (cl != cr) {
+                    const double x0 = (double)c.X[sp];
+                    const double x1 = (double)c.X[sp + 1];
+                    const double den = round24_even(x1 - x0);
+                    const double ip = (ctr - x0) / den;
+                    const uint32_t pr = c.IMGP[cr + 1];
+                    const double om = 1.0 - ip;
+                    double a = v0 * om, b = u8_to_f64(pr & 255u) * ip;
+                    v0 = a + b;
+                    a = v1 * om; b = u8_to_f64((pr >> 8) & 255u) * ip;
+                    v1 = a + b;
+                    a = v2 * om; b = u8_to_f64((pr >> 16) & 255u) * ip;
+                    v2 = a + b;
+                }
+                t0 = v0 * sig; t1 = v1 * sig; t2 = v2 * sig;
+                have = true;
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) ok = false;
+        const uint32_t hv = __ballot_sync(0xffffffffu, have);
+        const int nv = imin_(32, k1 - kb + 1);
+        for (int j = 0; j < nv; ++j) {
+            const double u0 = shfl_f64(t0, j), u1 = shfl_f64(t1, j), u2 = shfl_f64(t2, j);
+            if (hv & (1u << j)) {
+                c0 = round24_fp(c0 + u0);
+                c1 = round24_fp(c1 + u1);
+                c2 = round24_fp(c2 + u2);
+            }
+        }
+    }
+    return pack3((int)c0, (int)c1, (int)c2) | (ok ? 0u : kGaveUp);
+}
+#endif
+
 // ------------------------------------------------------------------ float32 path
 CS_HD float u8f(uint32_t p, int ch) {
 #ifdef __CUDA_ARCH__

@@ -270,6 +270,14 @@ __global__ void __launch_bounds__(kExactThreads) k_polylines_exact(const WarpArg
 // ------------------------------------------------------------------------------------------
 // tile kernel
 // ------------------------------------------------------------------------------------------
+#ifdef CS_POLY_TIMING
+__device__ unsigned long long g_poly_ticks[16];
+__device__ __forceinline__ long long cs_clock() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
+#define CS_TICK(n) do { if (threadIdx.x == 0) { long long now_ = cs_clock(); atomicAdd(&g_poly_ticks[n], (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#else
+#define CS_TICK(n) do { } while (0)
+#endif
+
 struct PolyGeom {             // per eye
     int tile_w[2];            // output columns per tile (>= W: the row is one tile and the window is the whole row)
     int ext[2];               // buckets start this many columns left of the tile (list replays walk back through a fold)
@@ -297,6 +305,9 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = a.w, tile = blockIdx.x, y = blockIdx.y, frame = blockIdx.z >> 1, eye = blockIdx.z & 1;
     if (a.eye[eye].passthrough || tile >= g.ntiles[eye]) return;
+#ifdef CS_POLY_TIMING
+    long long tick_ = cs_clock();
+#endif
 
     // ---- geometry: own output columns [o0, o0 + own), buckets [t0, t0 + tw), source window [s0, s0 + w)
     int t0 = 0, tw = W, own = W, s0 = 0, w = W;
@@ -328,10 +339,10 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     uint16_t* START = LIST + NP;                                 // [SCAP + 8]
     __shared__ float s_wa[32], s_wb[32];
     __shared__ int s_wr[32];
-    __shared__ int s_nslow, s_nhard, s_next;
+    __shared__ int s_nslow, s_nhard, s_next, s_nflag;
     __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
     if (t == 0) {
-        s_nslow = 0; s_nhard = 0; s_next = 0;
+        s_nslow = 0; s_nhard = 0; s_next = 0; s_nflag = 0;
         s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;
         s_tab.START = START; s_tab.w = w; s_tab.npts = npts; s_tab.nsg = nsg; s_tab.t0 = t0;
     }
@@ -407,6 +418,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (c0 + CPT == w && vec) IMGP[1 + w] = iv[CPT - 1];
     }
 
+    CS_TICK(0);
     // ---- B: prefix max / suffix min of x in source order (per-thread totals here, per-point values in C)
     float em, en;
     {
@@ -427,10 +439,19 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (lane == 31) s_wa[wid] = im;
         if (lane == 0) s_wb[wid] = in_;
         __syncthreads();
+        CS_TICK(1);
+        {   // totals of the other warps: one scan over the NW per-warp values
+            float wa = (lane < NW) ? s_wa[lane] : -INFINITY, wb = (lane < NW) ? s_wb[lane] : INFINITY;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            if (q < wid) em = fmaxf(em, s_wa[q]);
-            if (q > wid) en = fminf(en, s_wb[q]);
+            for (int o = 1; o < NW; o <<= 1) {
+                const float u = __shfl_up_sync(0xffffffffu, wa, o);
+                if (lane >= o) wa = fmaxf(wa, u);
+                const float d = __shfl_down_sync(0xffffffffu, wb, o);
+                if (lane + o < 32) wb = fminf(wb, d);
+            }
+            const float ea = __shfl_sync(0xffffffffu, wa, (wid + 31) & 31), eb = __shfl_sync(0xffffffffu, wb, (wid + 1) & 31);
+            if (wid > 0) em = fmaxf(em, ea);
+            if (wid < NW - 1) en = fminf(en, eb);
         }
         TMX[t] = fmaxf(em, m);
         TMN[t] = fminf(en, n);
@@ -479,6 +500,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
                 if (slow & (1u << e)) LIST[base++] = (uint16_t)(i0 + e);
         }
         __syncthreads();
+        CS_TICK(2);
         const int nslow = s_nslow;
         if (nslow) {
             // thread blocks of 8 points outwards from the point's own; a block is skipped, and the walk ends, as soon as
@@ -507,6 +529,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
                 RNK[i] = (uint16_t)rr;
             }
             __syncthreads();
+            CS_TICK(3);
             const uint4 pk = *reinterpret_cast<const uint4*>(RNK + i0);
             r[0] = pk.x & 0xFFFF; r[1] = pk.x >> 16; r[2] = pk.y & 0xFFFF; r[3] = pk.y >> 16;
             r[4] = pk.z & 0xFFFF; r[5] = pk.z >> 16; r[6] = pk.w & 0xFFFF; r[7] = pk.w >> 16;
@@ -526,6 +549,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (t == 0) { SX[0] = (float)(-1.0 * W); SID[0] = 0; END16[0] = (uint16_t)r[0]; }
     }
     __syncthreads();
+    CS_TICK(4);
 
     // ---- D: REACH = prefix max of END in sorted order; bucket starts; intervals with a single candidate
     {
@@ -560,9 +584,17 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (lane == 0) emr = 0;
         if (lane == 31) s_wr[wid] = im;
         __syncthreads();
+        CS_TICK(5);
+        {
+            int wr = (lane < NW) ? s_wr[lane] : 0;
 #pragma unroll
-        for (int q = 0; q < NW; ++q)
-            if (q < wid) emr = max(emr, s_wr[q]);
+            for (int o = 1; o < NW; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, wr, o);
+                if (lane >= o) wr = max(wr, u);
+            }
+            const int er0 = __shfl_sync(0xffffffffu, wr, (wid + 31) & 31);
+            if (wid > 0) emr = max(emr, er0);
+        }
         uint32_t wsp[8];
         uint32_t hard = 0;
 #pragma unroll
@@ -601,6 +633,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (k0 <= npts - 1 && npts - 1 < k0 + 8) START[tw + 2] = (uint16_t)npts;
     }
     __syncthreads();
+    CS_TICK(6);
 
     Tab tab;   // register copy for the inlined float32 path
     tab.X = X; tab.SX = SX; tab.ER = ER; tab.SID = SID; tab.WSP = WSP; tab.Q = Q; tab.IMGP = IMGP; tab.START = START;
@@ -613,12 +646,14 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         }
     }
     __syncthreads();
+    CS_TICK(7);
 
     // ---- E: sweep.  Warps take 32-column blocks from a shared counter (blocks inside folds cost several times more).
+    // Columns the float32 path cannot certify are listed and redone afterwards, all at once: inside the sweep each of
+    // them would stall its whole warp for longer than a block takes, and the slowest warp sets the CTA's lifetime.
     uint32_t* out = a.out[eye] + row_off + t0;
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
     const bool all_exact = (mode_flags & 8) != 0;
-    bool give_up = false;
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(&s_next, 1);
@@ -628,12 +663,26 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         if (col >= tw) continue;
         uint32_t px = 0;
         const bool ok = poly::fast_column<SHARP>(tab, col, &px) && !all_exact;
-        if (!ok) {
-            px = poly::exact_column<SHARP>(s_tab, col);
-            if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
-        }
-        out[col] = px;
+        if (ok) out[col] = px;
+        else LIST[atomicAdd(&s_nflag, 1)] = (uint16_t)col;
     }
+    CS_TICK(8);
+    __syncthreads();
+    CS_TICK(9);
+    bool give_up = false;
+    {
+        const int nflag = s_nflag;
+        for (int q = wid; q < nflag; q += NW) {     // one column per warp at a time
+            const int col = LIST[q];
+            uint32_t px = poly::exact_column_warp<SHARP>(s_tab, col);
+            if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
+            if (lane == 0) out[col] = px;
+        }
+#ifdef CS_POLY_TIMING
+        if (t == 0) { atomicAdd(&g_poly_ticks[12], (unsigned long long)nflag); atomicAdd(&g_poly_ticks[13], 1ull); }
+#endif
+    }
+    CS_TICK(10);
     if (give_up) {
         // a list replay did not fit its budget (or its history starts left of this tile): the row is redone sequentially
         const int rowid = (frame * 2 + eye) * a.h + y;
@@ -693,7 +742,9 @@ static bool plan_for(int nw, const WarpArgs& a, bool sharp, bool force_tiles, Po
         p->g.hi_off[eye] = (int)ceil(-a.eye[eye].sep_px + (reach + 4.0));
         if (!force_tiles && a.w <= cap_cols) {
             p->g.ntiles[eye] = 1;
-            p->cost += 0.45 + 0.55 * (double)(np / ppc) / a.w;
+            // whole rows have no window overlap, and large CTAs keep the warps of an SM sub-partition in the same code
+            // (measured: 16-warp whole rows 2.63 ms vs 4-warp tiles 2.85 ms per 16 frames of 1080p sharp)
+            p->cost += 0.40 + 0.55 * (double)(np / ppc) / a.w;
         } else {
             const int rmax = (int)ceil(reach);
             const int ext = 2 * rmax + 8;                       // a fold is at most 2 * reach wide
@@ -734,6 +785,13 @@ static cudaError_t launch_tiles(const WarpArgs& a, const PolyPlan& p, int* count
     if (occ == 2) return launch_tiles_occ<NW, SHARP, 512>(a, p, counters, flags, list, s);
     return launch_tiles_occ<NW, SHARP, 1024>(a, p, counters, flags, list, s);
 }
+
+#ifdef CS_POLY_TIMING
+extern "C" __attribute__((visibility("default"))) void cs_poly_ticks(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_poly_ticks, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_poly_ticks, z, sizeof(z)); }
+}
+#endif
 
 // flags bit 0 = replay every row with the sequential kernel, bit 2 = force 64-column tiles, bit 3 = every column through
 // exact_column (tests); bits 8-15 = CTA size in warps (0 = choose)

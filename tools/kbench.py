@@ -60,6 +60,14 @@ def main():
     k_n = (ctypes.c_longlong * nk)()
     lib.cs_profile_collect(k_ms, k_n)
     ks = {lib.cs_profile_kernel_name(i).decode(): round(k_ms[i] / a.steps, 3) for i in range(nk) if k_n[i] > 0}
+    if hasattr(lib, "cs_poly_ticks") or True:
+        try:
+            tk = (ctypes.c_ulonglong * 16)()
+            lib.cs_poly_ticks(tk, 1)
+            tot = sum(tk[:11]) or 1
+            print("   poly ticks share:", " ".join(f"{i}:{100.0 * tk[i] / tot:.1f}%" for i in range(11)), f"(total {tot / 1e9:.3f} Gcycles of thread 0; {tk[13]} CTAs, {tot / max(tk[13], 1):.0f} cycles each, {tk[12] / max(tk[13], 1):.2f} uncertified columns per CTA)")
+        except AttributeError:
+            pass
     print(f"{a.tag} {a.fill} {w}x{h} x{n}: {n / ms * 1e3:9.1f} fps  {ms:7.3f} ms/step  {ks}", flush=True)
 
 
