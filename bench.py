@@ -53,6 +53,11 @@ def parse_args():
     ap.add_argument("--fill", default=NODE_PARAMS["fill_technique"])
     ap.add_argument("--mode", default="left-right")
     ap.add_argument("--divergence", type=float, default=3.5)
+    ap.add_argument("--balance", type=float, default=0.0, help="stereo_balance (BASELINE config 5: 0.5)")
+    ap.add_argument("--separation", type=float, default=0.0)
+    ap.add_argument("--convergence", type=float, default=0.5)
+    ap.add_argument("--strong-frames", type=int, default=96, help="frames of the fixed batch of the strong-scaling leg (0 = skip)")
+    ap.add_argument("--no-extra-e2e", action="store_true", help="skip the pageable-input / large-output e2e legs")
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel sequence (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU baseline sample")
@@ -61,14 +66,22 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_frames(n, h, w, seed):
+def make_frames(n, h, w, seed, first=0):
+    """Frames [first, first + n) of the synthetic video: four distinct seeded frames, repeated with a horizontal roll that
+    grows with the global frame index -- cheap to generate, different content in every frame, and every rank can produce
+    any frame of the global batch on its own."""
     from comfystereo_b200 import synthetic as syn
-    # a few distinct frames, tiled: generation cost stays bounded, content still differs frame to frame
-    base = min(n, 4)
+    base = 4
     img = syn.make_image(base, h, w, seed=seed)
     dep = syn.make_depth(base, h, w, "scene", seed=seed)
-    reps = -(-n // base)
-    return np.tile(img, (reps, 1, 1, 1))[:n], np.tile(dep, (reps, 1, 1, 1))[:n]
+    oi = np.empty((n, h, w, 3), np.float32)
+    od = np.empty((n,) + dep.shape[1:], np.float32)
+    for i in range(n):
+        g = first + i
+        roll = (g // base) * 8 % w
+        oi[i] = np.roll(img[g % base], roll, axis=1) if roll else img[g % base]
+        od[i] = np.roll(dep[g % base], roll, axis=1) if roll else dep[g % base]
+    return oi, od
 
 
 def peaks():
@@ -128,7 +141,7 @@ def cpu_baseline(args, frames):
     orc.lib()
     orc.set_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     img, dep = make_frames(frames, args.height, args.width, seed=100)
-    params = dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence)
+    params = node_params(args)
     orc.node_generate(img[:1], dep[:1], **params)
     t0 = time.perf_counter()
     orc.node_generate(img, dep, **params)
@@ -165,12 +178,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def node_params(args):
+    return dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence,
+                stereo_balance=args.balance, separation=args.separation, convergence_point=args.convergence)
+
+
 def workload_config(args, frames):
     return {"workload": f"{args.width}x{args.height} {args.fill}, depth_map_blur on (strength 20, threshold 20, "
-                        f"falloff 2.0, vert 6), convergence 0.5, divergence {args.divergence}, exponent 2, {args.mode} "
+                        f"falloff 2.0, vert 6), convergence {args.convergence}, divergence {args.divergence}, "
+                        f"stereo_balance {args.balance}, separation {args.separation}, exponent 2, {args.mode} "
                         f"(BASELINE.json configs[1] as a batch)",
             "frames_per_gpu_per_step": frames, "l2": "inputs+outputs per step exceed the 126 MB L2 many times over "
-                                                     "(no flush needed)", "sharding": "frame-wise, no collective"}
+                                                     "(no flush needed)"}
+
+
+def host_copy_bandwidth(lib):
+    """GB/s (read + write bytes) the host's memory system gives a team of threads streaming a large buffer into
+    another with non-temporal stores -- the same loop the host path's result expansion runs."""
+    return float(lib.cs_host_stream_bandwidth(1 << 30, 0))
 
 
 def main():
@@ -196,9 +221,12 @@ def main():
     n, h, w = args.frames, args.height, args.width
     key = engine.FILL_NAME_TO_KEY.get(args.fill, "gpu_warp")
     group = min(NODE_PARAMS["batch_size"], n) if key == "gpu_warp" else 0
-    p = engine.make_params(key, args.mode, args.divergence, 0.0, 0.0, 0.5, 2.0, True, 20.0, 20.0, 2.0, 6, group_size=group)
-    # every rank gets the same frames: weak scaling means identical work per GPU (polylines cost depends on content)
-    img_np, dep_np = make_frames(n, h, w, seed=0)
+    p = engine.make_params(key, args.mode, args.divergence, args.separation, args.balance, args.convergence, 2.0, True,
+                           20.0, 20.0, 2.0, 6, group_size=group)
+    # Frame-wise sharding: the global batch of n * world frames is cut into contiguous ranges with
+    # engine.shard_range; this rank generates and processes only its own slice, no collective on the data path.
+    glo, ghi = engine.shard_range(n * world, rank, world)
+    img_np, dep_np = make_frames(ghi - glo, h, w, seed=0, first=glo)
     img_h = torch.from_numpy(img_np).pin_memory()
     dep_h = torch.from_numpy(dep_np).pin_memory()
     img_d, dep_d = img_h.to(dev), dep_h.to(dev)
@@ -237,6 +265,59 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms_total / args.steps
     fps = world * n / (ms_per_step * 1e-3)
+
+    # ---- in-order assembly check (N > 1): two frames owned by other ranks travel to rank 0 (the only transfers of the
+    # whole run, outside the timed region) and must equal rank 0's own single-GPU result for the same global frame
+    sharding = {"global_frames": n * world, "partition": "engine.shard_range: contiguous frame ranges, no collective"}
+    if world > 1:
+        samples = sorted({(n * world) // 2, n * world - 1})
+        ok = True
+        for g in samples:
+            owner = g // n
+            if rank == owner and owner != 0:
+                dist.send(outs[0][g - glo].contiguous(), dst=0)
+            if rank == 0:
+                if owner == 0:
+                    got = outs[0][g - glo]
+                else:
+                    got = torch.empty(s_shape[1:], dtype=torch.float32, device=dev)
+                    dist.recv(got, src=owner)
+                fi, fd = make_frames(1, h, w, seed=0, first=g)
+                want = engine.stereo_batch_device(torch.from_numpy(fi).to(dev), torch.from_numpy(fd).to(dev), p)[0][0]
+                ok = ok and bool(torch.equal(got, want))
+        if rank == 0:
+            assert ok, "a frame computed by another rank differs from the single-GPU result"
+            sharding["verified_frames"] = samples
+            sharding["verified"] = "frames owned by other ranks == rank 0's single-GPU result, bit for bit"
+        barrier()
+
+    # ---- strong scaling: one fixed batch (BASELINE config 3's shape: a video batch sharded frame-wise over the GPUs)
+    strong = None
+    if args.strong_frames > 0:
+        gs = args.strong_frames
+        slo, shi = engine.shard_range(gs, rank, world)
+        if shi > slo:
+            si, sd = make_frames(shi - slo, h, w, seed=0, first=slo)
+            si_d, sd_d = torch.from_numpy(si).to(dev), torch.from_numpy(sd).to(dev)
+            so = engine.stereo_batch_device(si_d, sd_d, p)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        reps = 3
+        for _ in range(reps):
+            if shi > slo:
+                engine.stereo_batch_device(si_d, sd_d, p, out=so)
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"global_frames": gs, "value": gs * reps / (float(t.item()) * 1e-3), "unit": "frames/s",
+                  "frames_per_gpu": -(-gs // world), "note": "fixed batch, frame-sharded; divide by the N=1 line's value "
+                  "of this key for strong-scaling efficiency"}
+        if shi > slo:
+            del si_d, sd_d, so
+        torch.cuda.empty_cache()
 
     # ---- per-kernel CUDA-event durations over the same steps (separate pass so `value` carries no event overhead)
     lib.cs_profile_enable(1)
@@ -284,7 +365,7 @@ def main():
                     "share_of_step": d_ms / total_k_ms,
                     "path": {"bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                             "note": "whole step: 80 B/px algorithmic I/O (SURVEY.md 8d) / step time"},
+                             "note": f"whole step: {BYTES_PER_PX[cls]} B/px algorithmic I/O (SURVEY.md 8d) / step time"},
                     "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
                                     "share": v[0] / total_k_ms,
                                     "gbs": k_bytes_px.get(k, 0) * px_step * args.steps / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None}
@@ -314,37 +395,63 @@ def main():
     e2e = None
     if not args.no_e2e:
         node = StereoImageNode()
-        params = dict(NODE_PARAMS, fill_technique=args.fill, modes=args.mode, divergence=args.divergence)
-
-        def e2e_step():
-            o = node.generate(img_h, dep_h, **params)
-            return float(o[3][0, 0, 0])   # touch the result on the host
-
+        params = node_params(args)
         # the node shards over every visible device from one process; under torchrun each rank owns one GPU
         os.environ.setdefault("COMFYSTEREO_SINGLE_DEVICE", "1")
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt.item())
+
+        def e2e_rate(ih, dh, steps):
+            def one():
+                o = node.generate(ih, dh, **params)
+                return float(o[3][0, 0, 0])   # touch the result on the host
+            for _ in range(2):
+                one()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                one()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
+
+        dt = e2e_rate(img_h, dep_h, args.e2e_steps)
         h2d = img_h.numel() * 4 + dep_h.numel() * 4
         d2h = sum(int(np.prod(s)) for s in (s_shape, d_shape, d_shape, m_shape)) * 4
         e2e = {"value": world * n * args.e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "api": "StereoImageNode.generate (CPU tensors in/out) -> cs_stereo_batch_host"}
+               "api": "StereoImageNode.generate (CPU tensors in/out) -> cs_stereo_batch_host", "inputs": "page-locked"}
+        bus = d2h
         if _lib.lib().cs_host_compact_enabled():
             # the result tensors hold d2h_bytes_per_step; of those, the depth outputs (3 identical channels) and the
             # mask (0/1) crossed PCIe as one channel / one byte per pixel and were expanded by host threads
             # (depth: the byte k of k/255 for the CPU techniques, one float for GPU Warp; mask: one byte)
-            dbytes = 4 if engine.FILL_NAME_TO_KEY.get(args.fill, 'gpu_warp') == 'gpu_warp' else 1
-            e2e["d2h_bus_bytes_per_step"] = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * dbytes + int(np.prod(m_shape))
+            dbytes = 4 if key == 'gpu_warp' else 1
+            bus = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * dbytes + int(np.prod(m_shape))
+            e2e["d2h_bus_bytes_per_step"] = bus
             e2e["transport"] = "compact depth/mask"
+        # how close the call is to what the host's memory system can move: DMA reads of the inputs, DMA writes of what
+        # crossed the bus, and the expansion's reads and writes of the compacted outputs
+        host_bw = host_copy_bandwidth(lib) if rank == 0 else None
+        if host_bw:
+            host_bytes = h2d + bus + ((bus - int(np.prod(s_shape)) * 4) + (d2h - int(np.prod(s_shape)) * 4) if bus != d2h else 0)
+            e2e["host_bytes_per_step"] = host_bytes
+            e2e["host_copy_gbs"] = host_bw
+            e2e["host_frac"] = (host_bytes * world / (dt / args.e2e_steps)) / 1e9 / host_bw
+            e2e["host_note"] = "host DRAM bytes the call moves per second (all ranks) / the host's streaming-copy bandwidth " \
+                               "measured in this run (one process, all threads, non-temporal stores)"
+        if world == 1 and not args.no_extra_e2e:
+            # what ComfyUI really passes: pageable inputs; and a result too large to be page-locked (> 4 GiB)
+            ip, dp = torch.from_numpy(img_np.copy()), torch.from_numpy(dep_np.copy())
+            dtp = e2e_rate(ip, dp, args.e2e_steps)
+            e2e["pageable_inputs"] = {"value": n * args.e2e_steps / dtp, "unit": "frames/s"}
+            big = 96
+            bi, bd = make_frames(big, h, w, seed=0)
+            bi, bd = torch.from_numpy(bi), torch.from_numpy(bd)
+            dtl = e2e_rate(bi, bd, 1)
+            e2e["large_batch"] = {"value": big / dtl, "unit": "frames/s", "frames": big,
+                                  "note": "pageable inputs, 11 GB of results (beyond the 4 GiB page-lock limit of the python host)"}
+            del bi, bd
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -355,14 +462,16 @@ def main():
                          f"{dt:.2f} s"}
 
     if rank == 0:
+        cfg = workload_config(args, n)
+        cfg["sharding"] = sharding
         line = {
             "metric": "1080p stereo frames/s", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n),
+            "config": cfg,
             "mpix_per_s": fps * h * w / 1e6,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "single_frame_latency": latency,
+            "roofline": roofline, "cpu_baseline": cpu, "single_frame_latency": latency, "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -66,6 +66,7 @@ SIGNATURES = {
     "cs_stereo_batch_host": (_I, [_PP, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
     "cs_host_release": (None, []),
     "cs_host_compact_enabled": (_I, []),
+    "cs_host_stream_bandwidth": (_D, [_SZ, _I]),
     "cs_launch_count": (ctypes.c_longlong, [_I]),
     "cs_polylines_status": (_I, [_PP, _I, _I, _I, _P, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "cs_set_test_flags": (None, [_I]),

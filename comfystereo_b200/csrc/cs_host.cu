@@ -271,6 +271,42 @@ extern "C" {
 
 int cs_host_compact_enabled(void) { return compact_transport(host_share()) ? 1 : 0; }
 
+// Streaming-copy bandwidth of this host (GB/s, read + write bytes): `threads` threads (0 = what one pipeline may use)
+// copy `bytes` from one buffer to another with the non-temporal stores of the expansion loops, best of three.
+// bench.py relates the end-to-end rate to it (e2e.host_frac).
+double cs_host_stream_bandwidth(size_t bytes, int threads) {
+    if (bytes < (1u << 20)) bytes = 1u << 20;
+    bytes &= ~(size_t)63;
+    int nt = threads > 0 ? threads : host_share();
+    if (nt > 64) nt = 64;
+    float* a = (float*)aligned_alloc(64, bytes);
+    float* b = (float*)aligned_alloc(64, bytes);
+    if (!a || !b) { free(a); free(b); return 0.0; }
+    const size_t nf = bytes / 4;
+    auto work = [&](int t, int pass) {
+        const size_t lo = (nf * t / nt) & ~(size_t)15, hi = (t == nt - 1) ? nf : ((nf * (t + 1) / nt) & ~(size_t)15);
+        if (pass == 0) { for (size_t i = lo; i < hi; ++i) { a[i] = (float)i; b[i] = 0.0f; } return; }   // first touch
+        size_t i = lo;
+#if defined(__SSE2__)
+        for (; i + 4 <= hi; i += 4) _mm_stream_ps(b + i, _mm_load_ps(a + i));
+        _mm_sfence();
+#endif
+        for (; i < hi; ++i) b[i] = a[i];
+    };
+    double best = 0.0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t, pass);
+        work(0, pass);
+        for (auto& t : th) t.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (pass > 0 && dt > 0.0) best = std::max(best, 2.0 * (double)bytes / dt / 1e9);
+    }
+    free(a); free(b);
+    return best;
+}
+
 void cs_host_release(void) {
     for (int i = 0; i < 16; ++i) {
         std::lock_guard<std::mutex> lk(g_mu[i]);

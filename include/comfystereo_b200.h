@@ -193,6 +193,11 @@ CS_API void cs_host_release(void);
  * COMFYSTEREO_COMPACT_D2H=0/1 says.  The tensors the caller receives are the same either way. */
 CS_API int cs_host_compact_enabled(void);
 
+/* Measurement aid for bench.py (e2e.host_frac): GB/s (read + write) that `threads` host threads (0 = what one
+ * pipeline of cs_stereo_batch_host may use) reach copying `bytes` with the non-temporal stores of the host path's
+ * expansion loops.  No GPU involved. */
+CS_API double cs_host_stream_bandwidth(size_t bytes, int threads);
+
 /* Number of kernel launches issued by this library (process-wide) since the last reset
  * (bench.py reports it as gpu_launches). */
 CS_API long long cs_launch_count(int reset);

@@ -1,12 +1,12 @@
 #!/bin/bash
 # Device-resident throughput of the five BASELINE.json configs (+ the other techniques at 1080p) -> gpurun_out/configs.jsonl
 out=gpurun_out/configs.jsonl; : > $out
-run() { timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>/dev/null | tail -1 >> $out; }
+run() { timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --strong-frames 0 "$@" 2>/dev/null | tail -1 >> $out; }
 run --height 512 --width 512 --frames 64 --fill "Fill - Naive"
 run --fill "Fill - Polylines Sharp"
 run --fill "Imperfect fill - Hybrid Edge"
 run --height 2160 --width 3840 --frames 8 --fill "GPU Warp (Fast)" --mode red-cyan-anaglyph --divergence 10
-run --height 3840 --width 7680 --frames 2 --fill "Fill - Polylines Sharp" --divergence 4.5
+run --height 3840 --width 7680 --frames 2 --fill "Fill - Polylines Sharp" --balance 0.5
 for f in "GPU Warp (Fast)" "No fill" "No fill - Reverse projection" "Fill - Naive" "Fill - Naive interpolating" "Fill - Polylines Soft" "Fill - Post-fill" "Fill - Reverse projection with Post-fill" "Fill - Hybrid Edge with fill"; do run --fill "$f"; done
 python - <<'PY'
 import json
