@@ -347,11 +347,12 @@ CS_HD float u8f(uint32_t p, int ch) {
 //                      2^-17   significance: d = to' - from' is exact (both inside one pixel), d - 2e-7f rounds once
 //                              (<= 2^-25), times a colour <= 255
 //                      2^-17   the interpolated colour (one fmaf, values < 256), times a significance <= 1
-//   per column         255 * 5e-7 = 1.3e-4   interpolation parameter: two float32 roundings of the numerator (the
-//                              centre itself is from' + d / 2 exactly: the two epsilons cancel), the approximate
-//                              reciprocal and product (<= 2 ulp); its weight is the significance, which sums to <= 1
-// kErrVisit / kErrColumn round these up by ~30 %.
-constexpr float kErrVisit = 4.0e-5f, kErrColumn = 1.7e-4f;
+//   per column         255 * 3.0e-7 = 7.7e-5   interpolation parameter: two float32 roundings of the numerator (the
+//                              centre itself is from' + d / 2 exactly: the two epsilons cancel; 2 * 2^-24), the approximate
+//                              reciprocal (rcp.approx: 2^-23) and the product (2^-24); its weight is the significance,
+//                              which sums to <= 1 per column
+// kErrVisit = 4 * 2^-17 and kErrColumn rounded up.
+constexpr float kErrVisit = 3.2e-5f, kErrColumn = 9.0e-5f;
 
 CS_HD float fast_rcp(float a) {
 #ifdef __CUDA_ARCH__
@@ -415,40 +416,68 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
 // interval by more than any rounding could matter.  Returns the WSP entry.
 template <bool SHARP>
 CS_HD uint32_t classify_interval(const Tab& c, int k) {
-    int cnt = 0, j1 = 0, j2 = 0;
+    constexpr int kMaxCand = 4;
+    int cnt = 0, j0 = 0, j1 = 0, j2 = 0, j3 = 0;
     for (int j = k; j >= 0; --j) {
         const uint32_t er = c.ER[j];
         if ((int)(er >> 16) <= k) break;            // nothing at or before j reaches past point k
         if ((int)(er & 0xFFFFu) > k) {
-            if (cnt == 0) j1 = j; else if (cnt == 1) j2 = j;
+            if (cnt == 0) j0 = j; else if (cnt == 1) j1 = j; else if (cnt == 2) j2 = j; else if (cnt == 3) j3 = j;
             ++cnt;
         }
     }
     const uint32_t own = (uint32_t)c.SID[k];
-    if (cnt == 1) return (uint32_t)c.SID[j1];
-    if (cnt != 2) return own | kUnresolved;
-    // Interpolated closeness is linear in the centre, so a candidate that leads at both ends of the interval leads at
-    // every centre inside.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active segment, and ip < 1
-    // can only fail (float32 rounding of x1 - x0) for long segments that end at or just beyond this interval's right
-    // point -- those stay unresolved and are decided per visit in FP64.
-    const int spA = (int)c.SID[j1], spB = (int)c.SID[j2];
-    const float aq0 = c.Q[pt_slot<SHARP>(spA)], aq1 = c.Q[pt_slot<SHARP>(spA + 1)];
-    const float bq0 = c.Q[pt_slot<SHARP>(spB)], bq1 = c.Q[pt_slot<SHARP>(spB + 1)];
-    const float ax0 = c.SX[j1], ax1 = c.X[spA + 1], bx0 = c.SX[j2], bx1 = c.X[spB + 1];
-    const float bv = c.SX[k + 1];
-    const float ad = ax1 - ax0, bd = bx1 - bx0;
-    const bool safe = (ad < 2.0f || (ax1 - bv) > ad * 1.2e-7f) && (bd < 2.0f || (bx1 - bv) > bd * 1.2e-7f);
-    const float margin = 1e-3f + 1e-4f * fmaxf(fmaxf(aq0, aq1), fmaxf(bq0, bq1));
-    float a_lo = aq0, a_hi = aq0, b_lo = bq0, b_hi = bq0;
-    if (aq0 != aq1 || bq0 != bq1) {    // (two segments of constant closeness -- neighbouring pixels swapped -- need none of this)
-        const float av = c.SX[k];
-        const float ra = fast_rcp(ad), rb = fast_rcp(bd);
-        a_lo = aq0 + (av - ax0) * ra * (aq1 - aq0); a_hi = aq0 + (bv - ax0) * ra * (aq1 - aq0);
-        b_lo = bq0 + (av - bx0) * rb * (bq1 - bq0); b_hi = bq0 + (bv - bx0) * rb * (bq1 - bq0);
+    if (cnt == 1) return (uint32_t)c.SID[j0];
+    if (cnt < 1 || cnt > kMaxCand) return own | kUnresolved;
+    // Interpolated closeness is linear in the centre, so a candidate that leads every other one at both ends of the
+    // interval leads at every centre inside.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
+    // segment, and ip < 1 can only fail (float32 rounding of x1 - x0) for long segments that end at or just beyond this
+    // interval's right point -- those leave the interval unresolved, to be decided per visit in FP64.
+    const float av = c.SX[k], bv = c.SX[k + 1];
+    float lo[kMaxCand], hi[kMaxCand];
+    uint32_t sps[kMaxCand];
+    bool safe = true;
+    float qmax = 0.0f;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kMaxCand; ++q) {
+        const int j = (q == 0) ? j0 : (q == 1 ? j1 : (q == 2 ? j2 : j3));
+        lo[q] = -1.0f; hi[q] = -1.0f; sps[q] = 0;
+        if (q < cnt) {
+            const int sp = (int)c.SID[j];
+            const float q0 = c.Q[pt_slot<SHARP>(sp)], q1 = c.Q[pt_slot<SHARP>(sp + 1)];
+            const float x0 = c.SX[j], x1 = c.X[sp + 1];
+            const float d = x1 - x0;
+            safe = safe && (d < 2.0f || (x1 - bv) > d * 1.2e-7f);
+            float l = q0, h = q0;
+            if (q0 != q1) {     // (segments of constant closeness -- the two points of one pixel -- need none of this)
+                const float r = fast_rcp(d);
+                l = q0 + (av - x0) * r * (q1 - q0);
+                h = q0 + (bv - x0) * r * (q1 - q0);
+            }
+            lo[q] = l; hi[q] = h; sps[q] = (uint32_t)sp;
+            qmax = fmaxf(qmax, fmaxf(q0, q1));
+        }
     }
-    if (safe && a_lo > b_lo + margin && a_hi > b_hi + margin) return (uint32_t)spA;
-    if (safe && b_lo > a_lo + margin && b_hi > a_hi + margin) return (uint32_t)spB;
-    return own | kUnresolved;
+    const float margin = 1e-3f + 1e-4f * qmax;
+    // the leader at the left end must lead every other candidate by the margin at both ends
+    int best = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 1; q < kMaxCand; ++q)
+        if (q < cnt && lo[q] > lo[best]) best = q;
+    const float bl = (best == 0) ? lo[0] : (best == 1 ? lo[1] : (best == 2 ? lo[2] : lo[3]));
+    const float bh = (best == 0) ? hi[0] : (best == 1 ? hi[1] : (best == 2 ? hi[2] : hi[3]));
+    const uint32_t bs = (best == 0) ? sps[0] : (best == 1 ? sps[1] : (best == 2 ? sps[2] : sps[3]));
+    bool lead = safe;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < kMaxCand; ++q)
+        if (q < cnt && q != best) lead = lead && (bl > lo[q] + margin) && (bh > hi[q] + margin);
+    return lead ? bs : (own | kUnresolved);
 }
 
 }  // namespace poly
