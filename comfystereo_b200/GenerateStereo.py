@@ -3,8 +3,12 @@
 Identical widget schema (names, order, defaults, ranges), RETURN_TYPES / RETURN_NAMES / FUNCTION,
 `generate` signature and output conventions (four float32 CPU tensors: stereoscope [N,Ho,Wo,3],
 blurred_depthmap_left/right [N,H,W,3], no_fill_imperfect_mask [N,Hm,Wm]).  Inside, the whole batch is
-handed to the sm_100a library in one call: frames stream host -> GPU -> host in overlapped chunks,
-and are sharded frame-wise over every visible GPU when there is more than one.
+handed to the sm_100a library in one call: frames stream host -> GPU -> host in overlapped chunks
+(and are sharded frame-wise over the visible GPUs when COMFYSTEREO_MULTI_GPU is set).
+
+"GPU Warp (Fast)" reproduces the reference's forward_warp_gpu (SIG:277-450), which is what the reference runs when
+moderngl is not importable; with moderngl installed the reference switches to its OpenGL mesh rasteriser
+(forward_warp_mesh, SIG:1067-1071), whose output depends on the GL driver and is not reproduced here.
 """
 import os
 
@@ -51,7 +55,8 @@ class StereoImageNode:
                 "modes": (list(MODES),),
                 "fill_technique": (list(FILL_TECHNIQUES), {
                     "default": "GPU Warp (Fast)",
-                    "tooltip": "How disoccluded areas are treated. All techniques run as B200 CUDA kernels."}),
+                    "tooltip": "How disoccluded areas are treated. All techniques run as B200 CUDA kernels. "
+                               "GPU Warp (Fast) = the reference's scatter warp (forward_warp_gpu), not its moderngl mesh rasteriser."}),
             },
             "optional": {
                 "divergence": ("FLOAT", {"default": 4.5, "min": 0.05, "max": 15, "step": 0.01,
@@ -108,15 +113,22 @@ class StereoImageNode:
         else:
             if not torch.cuda.is_available():
                 raise RuntimeError("comfystereo_b200 needs a CUDA (sm_100a) device; it has no CPU fallback")
-            # one process driving every visible GPU -- unless this process is already one rank of a
-            # torch.distributed job (one process per GPU) or the user pinned it to a single device
-            single = os.environ.get("COMFYSTEREO_SINGLE_DEVICE", "0") == "1" or \
-                (torch.distributed.is_available() and torch.distributed.is_initialized())
-            ndev = 1 if single else torch.cuda.device_count()
+            # One GPU by default, like the reference.  COMFYSTEREO_MULTI_GPU=1 (or =<count>) lets this process shard the
+            # batch frame-wise over the visible GPUs -- opt-in, because every device then holds its own workspace and
+            # page-locked staging buffers (a shared server may not want that).  Never inside a torch.distributed job,
+            # where each rank owns one GPU already.
+            want = os.environ.get("COMFYSTEREO_MULTI_GPU", "0")
+            in_job = torch.distributed.is_available() and torch.distributed.is_initialized()
+            ndev = 1
+            if want not in ("", "0") and not in_job and os.environ.get("COMFYSTEREO_SINGLE_DEVICE", "0") != "1":
+                ndev = torch.cuda.device_count() if want == "1" else min(int(want), torch.cuda.device_count())
+            # progress per chunk of frames, as the reference reports it per frame / sub-batch (GS:173, GS:262)
             if ndev > 1 and total >= 2 * ndev:
-                outs = engine.stereo_batch_multi_gpu(image, depth, p, list(range(ndev)), resize_depth=True)
+                outs = engine.stereo_batch_multi_gpu(image, depth, p, list(range(ndev)), resize_depth=True, progress=pbar.update)
             else:
-                outs = engine.stereo_batch_host(image, depth, p, device=torch.cuda.current_device(), resize_depth=True)
+                outs = engine.stereo_batch_host(image, depth, p, device=torch.cuda.current_device(), resize_depth=True,
+                                                progress=pbar.update)
+            return outs
         pbar.update(total)
         return outs
 

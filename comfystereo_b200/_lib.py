@@ -45,6 +45,7 @@ _I = ctypes.c_int
 _D = ctypes.c_double
 _SZ = ctypes.c_size_t
 _PP = ctypes.POINTER(CsParams)
+PROGRESS_FN = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)   # cs_progress_fn
 
 # name -> (restype, argtypes); every symbol include/comfystereo_b200.h declares
 SIGNATURES = {
@@ -64,6 +65,7 @@ SIGNATURES = {
     "cs_compose": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cs_stereo_batch": (_I, [_PP, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "cs_stereo_batch_host": (_I, [_PP, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I]),
+    "cs_stereo_batch_host_progress": (_I, [_PP, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "cs_host_release": (None, []),
     "cs_host_compact_enabled": (_I, []),
     "cs_host_stream_bandwidth": (_D, [_SZ, _I]),
@@ -92,7 +94,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        if handle.cs_abi_version() != 2:
+        if handle.cs_abi_version() != 3:
             raise ImportError("libcomfystereo_b200.so: ABI version mismatch, rebuild it")
         _lib = handle
     return _lib

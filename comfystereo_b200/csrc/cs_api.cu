@@ -69,6 +69,9 @@ static int check_params(const cs_params* p) {
         if (p->blur_radius < 0 || p->blur_radius > kMaxBlurRadius)
             return fail(CS_ERR_UNSUPPORTED, "blur radius %d outside 0..%d", p->blur_radius, kMaxBlurRadius);
         if (p->blur_vert_smooth < 0) return fail(CS_ERR_ARG, "negative vert_smooth");
+        if (p->blur_vert_smooth > 15)
+            return fail(CS_ERR_UNSUPPORTED, "depth_blur_vert_smooth %d: this library supports 0..15 (the widget's range)", p->blur_vert_smooth);
+        if (p->blur_box > 4096) return fail(CS_ERR_UNSUPPORTED, "blur box %d wider than 4096 px is not supported", p->blur_box);
     }
     return CS_OK;
 }
@@ -134,7 +137,7 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
         ws.eye_out[0] = (uint32_t*)take(px * 4);
         ws.eye_out[1] = (uint32_t*)take(px * 4);
         if (p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP) {
-            ws.warp_scratch_bytes = polylines_scratch_bytes(chunk, h);
+            ws.warp_scratch_bytes = polylines_scratch_bytes(chunk, h, w);
             ws.warp_scratch = take(ws.warp_scratch_bytes);
         } else if (p->fill == CS_FILL_HYBRID_EDGE_PLUS) {
             ws.warp_scratch_bytes = hybrid_plus_scratch_bytes(chunk, h, w);
@@ -230,7 +233,7 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
     return CS_OK;
 }
 
-static int g_test_flags = 0;
+static std::atomic<int> g_test_flags{0};
 
 }  // namespace cs
 
@@ -267,7 +270,7 @@ size_t cs_workspace_bytes(const cs_params* p, int chunk, int h, int w) {
     return carve(p, chunk, h, w, nullptr).total;
 }
 
-void cs_set_test_flags(int flags) { g_test_flags = flags; }
+void cs_set_test_flags(int flags) { g_test_flags.store(flags); }
 
 int cs_profile_kernel_count(void) { return K_COUNT; }
 const char* cs_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }
@@ -338,7 +341,7 @@ int cs_shift_indices(const float* nd, int n, int h, int w, double div_px, double
 
 size_t cs_warp_fill_scratch_bytes(int n, int h, int w) {
     (void)w;
-    return align_up((size_t)n * sizeof(FrameStats)) + align_up(polylines_scratch_bytes(n, h)) +
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(polylines_scratch_bytes(n, h, w)) +
            align_up(hybrid_plus_scratch_bytes(n, h, w));
 }
 
@@ -354,7 +357,7 @@ int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int 
     char* rest = (char*)scratch + align_up((size_t)n * sizeof(FrameStats));
     CS_CUDA(launch_init_stats(st, n, s), "init_stats");
     CS_CUDA(launch_minmax(depth, n, (int64_t)h * w, st, s), "minmax");
-    CS_CUDA(cudaMemsetAsync(rest, 0, polylines_scratch_bytes(n, h), s), "memset");
+    CS_CUDA(cudaMemsetAsync(rest, 0, 64, s), "memset");
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.image_u8 = (const uint32_t*)image_u8;
@@ -369,12 +372,12 @@ int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int 
     a.eye[1].passthrough = 1;
     a.expo = exponent;
     a.conv = (float)convergence;
-    a.scratch = rest; a.scratch_bytes = polylines_scratch_bytes(n, h);
+    a.scratch = rest; a.scratch_bytes = polylines_scratch_bytes(n, h, w);
     if (fill == CS_FILL_HYBRID_EDGE_PLUS) {
-        a.scratch = rest + align_up(polylines_scratch_bytes(n, h));
+        a.scratch = rest + align_up(polylines_scratch_bytes(n, h, w));
         a.scratch_bytes = hybrid_plus_scratch_bytes(n, h, w);
     }
-    a.flags = g_test_flags;
+    a.flags = g_test_flags.load();
     cudaError_t e = launch_fill(a, s);
     if (e != cudaSuccess) return cuda_fail(e, "warp/fill");
     return CS_OK;
@@ -435,7 +438,10 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     {
         const bool sharp = p->fill == CS_FILL_POLYLINES_SHARP;
         const bool soft = p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_HYBRID_EDGE_PLUS;
-        const int wmax = sharp ? 8000 : (soft ? 12000 : (p->fill == CS_FILL_GPU_WARP ? 9000 : 16000));
+        // Polylines: rows of any width are tiled (only the 16-bit point indices of the sequential fallback bound them);
+        // the other techniques keep one row per CTA in shared memory
+        const bool plus = p->fill == CS_FILL_HYBRID_EDGE_PLUS;
+        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (p->fill == CS_FILL_GPU_WARP ? 9000 : 16000));
         if (w > wmax)
             return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
                         "(one row per CTA in shared memory)", w, wmax);
@@ -459,7 +465,7 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
         const size_t dpx = needs_resize(p, h, w) ? (size_t)p->depth_h * p->depth_w : px;
         rc = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * dpx * c, m, h, w, c,
                        stereo + (size_t)f0 * ho * wo * 3, depth_l + (size_t)f0 * px * 3, depth_r + (size_t)f0 * px * 3,
-                       mask + (size_t)f0 * hm * wm, ws, g_test_flags, s);
+                       mask + (size_t)f0 * hm * wm, ws, g_test_flags.load(), s);
         if (rc) return rc;
     }
     return CS_OK;

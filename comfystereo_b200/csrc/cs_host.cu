@@ -316,6 +316,12 @@ void cs_host_release(void) {
 
 int cs_stereo_batch_host(const cs_params* p, const float* image, const float* depth, int n, int h, int w, int c,
                          float* stereo, float* depth_l, float* depth_r, float* mask, int device) {
+    return cs_stereo_batch_host_progress(p, image, depth, n, h, w, c, stereo, depth_l, depth_r, mask, device, nullptr, nullptr);
+}
+
+int cs_stereo_batch_host_progress(const cs_params* p, const float* image, const float* depth, int n, int h, int w, int c,
+                                  float* stereo, float* depth_l, float* depth_r, float* mask, int device,
+                                  cs_progress_fn progress, void* user) {
 #define HOST_FAIL(code, ...) return cs::fail(code, __VA_ARGS__)
 #define HOST_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cs::fail(CS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
     if (!p || !image || !depth || !stereo || !depth_l || !depth_r || !mask) HOST_FAIL(CS_ERR_ARG, "cs_stereo_batch_host: NULL pointer");
@@ -407,7 +413,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             }
             const int f0 = pit * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = pit % kSlots;
             const auto c0 = std::chrono::steady_clock::now();
-            if (cudaEventSynchronize(cx.ev_out[sl]) != cudaSuccess) drain_rc = CS_ERR_CUDA;
+            if (cudaEventSynchronize(cx.ev_out[sl]) != cudaSuccess) { std::lock_guard<std::mutex> g(mu); drain_rc = CS_ERR_CUDA; }
             const auto c1 = std::chrono::steady_clock::now();
             if (bounce_out) parallel_copy(out_spans(f0, m, cx.h_out[sl]), team);
             if (compact)
@@ -429,10 +435,35 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
         std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& stop;
         ~Joiner() { if (t.joinable()) { { std::lock_guard<std::mutex> g(mu); stop = true; } cv.notify_all(); t.join(); } }
     } joiner{drainer, mu, cv, stop};
+    // an early error return must not leave copies into the caller's buffers in flight (they may be freed right after)
+    struct SyncOnError { bool ok = false; ~SyncOnError() { if (!ok) { cudaDeviceSynchronize(); (void)cudaGetLastError(); } } } sync_guard;
+
+    // Progress (GS:173, GS:262: the reference updates its bar per sub-batch / per frame): chunks are reported in order, on
+    // the calling thread, as soon as their results are complete in the caller's memory.
+    int reported = 0;
+    auto chunk_frames = [&](int ci) { const int f0 = ci * chunk; return (n - f0 < chunk) ? n - f0 : chunk; };
+    auto report_done = [&](int upto, bool wait) {    // chunks [reported, upto) -- only those already complete unless `wait`
+        while (reported < upto) {
+            bool done;
+            if (drain) {
+                std::unique_lock<std::mutex> g(mu);
+                if (wait) cv.wait(g, [&] { return drained > reported || drain_rc != CS_OK; });
+                done = drained > reported;
+            } else {
+                cudaEvent_t ev = cx.ev_out[reported % kSlots];
+                done = wait ? (cudaEventSynchronize(ev) == cudaSuccess) : (cudaEventQuery(ev) == cudaSuccess);
+            }
+            if (!done) break;
+            if (progress) progress(chunk_frames(reported), user);
+            ++reported;
+        }
+        (void)cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+    };
 
     for (int it = 0; it < nchunks; ++it) {
         {
             const int f0 = it * chunk, m = (n - f0 < chunk) ? n - f0 : chunk, sl = it % kSlots;
+            if (progress && it >= kSlots) report_done(it - kSlots + 1, false);
             if (drain && it >= kSlots) {   // the slot's host landing buffers must have been drained (chunk it - kSlots)
                 const auto w0 = std::chrono::steady_clock::now();
                 std::unique_lock<std::mutex> g(mu);
@@ -493,9 +524,10 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
             if (drain) { { std::lock_guard<std::mutex> g(mu); enqueued = it + 1; } cv.notify_all(); }
         }
     }
+    if (progress) report_done(nchunks, true);
     if (drain) {
         std::unique_lock<std::mutex> g(mu);
-        cv.wait(g, [&] { return drained >= nchunks; });
+        cv.wait(g, [&] { return drained >= nchunks || drain_rc != CS_OK; });
         if (drain_rc) HOST_FAIL(CS_ERR_CUDA, "pipeline: download failed");
     }
     if (const char* tr = getenv("COMFYSTEREO_HOST_TRACE"))
@@ -510,6 +542,7 @@ int cs_stereo_batch_host(const cs_params* p, const float* image, const float* de
     HOST_CUDA(cudaStreamSynchronize(cx.s_out));
     e = cudaGetLastError();
     if (e != cudaSuccess) HOST_FAIL(CS_ERR_CUDA, "pipeline: %s", cudaGetErrorString(e));
+    sync_guard.ok = true;
     return CS_OK;
 #undef HOST_FAIL
 #undef HOST_CUDA

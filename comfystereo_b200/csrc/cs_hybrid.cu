@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_merge_black(uint32_t* __restrict__ prim
 
 static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 size_t hybrid_plus_scratch_bytes(int n, int h, int w) {
-    return 2 * up256((size_t)n * h * w * 4) + up256(polylines_scratch_bytes(n, h));
+    return 2 * up256((size_t)n * h * w * 4) + up256(polylines_scratch_bytes(n, h, w));
 }
 
 cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s) {
@@ -229,7 +229,7 @@ cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s) {
     p.out[0] = reinterpret_cast<uint32_t*>(a.scratch);
     p.out[1] = reinterpret_cast<uint32_t*>((char*)a.scratch + eye_bytes);
     p.scratch = (char*)a.scratch + 2 * eye_bytes;
-    p.scratch_bytes = polylines_scratch_bytes(a.n, a.h);
+    p.scratch_bytes = polylines_scratch_bytes(a.n, a.h, a.w);
     if ((e = cudaMemsetAsync((char*)p.scratch + p.scratch_bytes - 16 * sizeof(int), 0, 16 * sizeof(int), s)) != cudaSuccess) return e;
     if ((e = launch_polylines(p, s)) != cudaSuccess) return e;
     const int64_t total = (int64_t)a.n * a.h * a.w;

@@ -171,7 +171,7 @@ cudaError_t launch_shift_indices(const float* nd, int n, int h, int w, double di
 cudaError_t launch_warp_rows(const WarpArgs& a, cudaStream_t s);       // none / naive / interp / inverse
 cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s);       // soft / sharp
 cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s);          // hybrid_edge (2 kernels)
-size_t polylines_scratch_bytes(int n, int h);
+size_t polylines_scratch_bytes(int n, int h, int w);
 size_t hybrid_plus_scratch_bytes(int n, int h, int w);
 cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s);     // hybrid_edge_plus (hybrid + polylines_soft + merge)
 cudaError_t launch_minmax(const float* src, int n, int64_t npx, FrameStats* stats, cudaStream_t s);

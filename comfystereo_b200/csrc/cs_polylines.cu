@@ -186,11 +186,14 @@ __device__ __forceinline__ void accumulate(float* color, uint32_t pl, uint32_t p
 // sequential sweep: one thread replays the reference's list semantics for a whole row
 // ------------------------------------------------------------------------------------------
 // row_list == nullptr: every (frame, eye, row); else the rows k_polylines listed (row id = (frame * 2 + eye) * h + y).
+// gtables != nullptr: rows too wide for a CTA's shared memory keep their tables in global scratch (one slice per CTA).
 __global__ void __launch_bounds__(kExactThreads) k_polylines_exact(const WarpArgs a, int sharp, int act_cap,
                                                                    const int* __restrict__ row_list,
                                                                    const int* __restrict__ row_count,
-                                                                   int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                                   int* __restrict__ status,
+                                                                   unsigned char* __restrict__ gtables, size_t gtable_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = gtables ? gtables + (size_t)blockIdx.x * gtable_bytes : smem_dyn;
     __shared__ int s_warp[32];
     const int w = a.w;
     const int total = row_list ? *row_count : a.n * 2 * a.h;
@@ -695,24 +698,53 @@ static size_t exact_smem(int w, int sharp, int act_cap) {
     size_t np2 = npts + (npts & 1);
     return npts * 4 + (size_t)w * 4 + (size_t)(w + 4) * 4 + np2 * 2 * 3 + (size_t)act_cap * 2;
 }
+constexpr int kExactGlobalGrid = 64;     // CTAs of the sequential kernel when its tables live in global scratch
+constexpr size_t kMaxSmem = 226 * 1024;   // dynamic shared memory a CTA may ask for here (1 KB left for static arrays)
+static long long exact_act_cap_ref(const WarpArgs& a) {
+    const double dmax = fmax(fabs(a.eye[0].div_px), fabs(a.eye[1].div_px));
+    return 5ll * (long long)dmax + 25;    // the reference's own list capacity, SIG:1947
+}
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 // scratch: [16] counters (0: status bits, 1: listed rows) + [n*2*h] row flags + [n*2*h] row list
-size_t polylines_scratch_bytes(int n, int h) { return ((size_t)n * 2 * h * 2 + 16) * sizeof(int); }
+//          (+ kExactGlobalGrid table slices for rows whose sequential-sweep tables exceed a CTA's shared memory)
+static size_t poly_header_bytes(int n, int h) { return align256(((size_t)n * 2 * h * 2 + 16) * sizeof(int)); }
+static size_t exact_gtable_bytes(int w) {
+    // sharp tables (the larger), active list of the largest capacity the widget ranges can ask for: |div_px| <= 0.3 w
+    return align256(exact_smem(w, 1, 0) + 2 * (size_t)(5 * (long long)(0.3 * w + 1) + 25));
+}
+size_t polylines_scratch_bytes(int n, int h, int w) {
+    size_t b = poly_header_bytes(n, h);
+    if (exact_smem(w, 1, 64) + 64 > kMaxSmem) b += (size_t)kExactGlobalGrid * exact_gtable_bytes(w);
+    return b;
+}
 
 static cudaError_t launch_exact(const WarpArgs& a, int sharp, bool listed, int* counters, int* list, cudaStream_t s) {
-    const size_t kMaxSmem = 227 * 1024;
-    double dmax = fmax(fabs(a.eye[0].div_px), fabs(a.eye[1].div_px));
-    long long cap_ref = 5ll * (long long)dmax + 25;    // the reference's own list capacity, SIG:1947
-    size_t base = exact_smem(a.w, sharp, 0);
-    if (base + 64 > kMaxSmem) return cudaErrorInvalidValue;
-    long long cap_fit = (long long)((kMaxSmem - base) / 2);
-    int act_cap = (int)(cap_ref < cap_fit ? cap_ref : cap_fit);
-    size_t es = exact_smem(a.w, sharp, act_cap);
-    if (es > 48 * 1024) cudaFuncSetAttribute(k_polylines_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
+    const long long cap_ref = exact_act_cap_ref(a);
+    const size_t base = exact_smem(a.w, sharp, 0);
     const int rows = a.n * 2 * a.h;
-    // listed rows are rare (usually none): a small grid that strides over the list
-    const int grid = listed ? (rows < 296 ? rows : 296) : rows;
+    unsigned char* gtables = nullptr;
+    size_t gbytes = 0, es = 0;
+    int act_cap, grid;
+    if (base + 64 <= kMaxSmem) {
+        const long long cap_fit = (long long)((kMaxSmem - base) / 2);
+        act_cap = (int)(cap_ref < cap_fit ? cap_ref : cap_fit);
+        es = exact_smem(a.w, sharp, act_cap);
+        if (es > 48 * 1024) cudaFuncSetAttribute(k_polylines_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
+        // listed rows are rare (usually none): a small grid that strides over the list
+        grid = listed ? (rows < 296 ? rows : 296) : rows;
+    } else {
+        // very wide rows: tables in global scratch, behind the header
+        gbytes = exact_gtable_bytes(a.w);
+        const size_t hdr = poly_header_bytes(a.n, a.h);
+        if (a.scratch_bytes < hdr + (size_t)kExactGlobalGrid * gbytes) return cudaErrorInvalidValue;
+        gtables = reinterpret_cast<unsigned char*>(a.scratch) + hdr;
+        const long long cap_fit = (long long)((gbytes - exact_smem(a.w, sharp, 0)) / 2);
+        act_cap = (int)(cap_ref < cap_fit ? cap_ref : cap_fit);
+        grid = rows < kExactGlobalGrid ? rows : kExactGlobalGrid;
+    }
     prof_begin(K_POLY_EXACT, s);
-    k_polylines_exact<<<grid, kExactThreads, es, s>>>(a, sharp, act_cap, listed ? list : nullptr, counters + 1, counters);
+    k_polylines_exact<<<grid, kExactThreads, es, s>>>(a, sharp, act_cap, listed ? list : nullptr, counters + 1, counters,
+                                                      gtables, gbytes);
     prof_end(K_POLY_EXACT, s);
     count_launch();
     return cudaGetLastError();
@@ -797,7 +829,7 @@ extern "C" __attribute__((visibility("default"))) void cs_poly_ticks(unsigned lo
 // exact_column (tests); bits 8-15 = CTA size in warps (0 = choose)
 cudaError_t launch_polylines(const WarpArgs& a, cudaStream_t s) {
     const bool sharp = a.fill == CS_FILL_POLYLINES_SHARP;
-    if (a.scratch_bytes < polylines_scratch_bytes(a.n, a.h)) return cudaErrorInvalidValue;
+    if (a.scratch_bytes < polylines_scratch_bytes(a.n, a.h, a.w)) return cudaErrorInvalidValue;
     if ((sharp ? 2 * (long long)a.w : (long long)a.w) + 2 > 65535) return cudaErrorInvalidValue;
     int* counters = reinterpret_cast<int*>(a.scratch);
     int* flags = counters + 16;

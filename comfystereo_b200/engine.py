@@ -67,23 +67,14 @@ def output_shapes(p, n, h, w):
     return (n, ho.value, wo.value, 3), (n, h, w, 3), (n, hm.value, wm.value)
 
 
-_ws_lock = threading.Lock()
-_workspaces = {}  # device index -> uint8 tensor
-
-
 def _workspace(device, nbytes):
-    with _ws_lock:
-        t = _workspaces.get(device.index)
-        if t is None or t.numel() < nbytes:
-            _workspaces.pop(device.index, None)
-            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            _workspaces[device.index] = t
-        return t
+    """Scratch for one call, from torch's caching allocator: it hands a block back only to allocations on the same
+    stream, so concurrent calls (other threads, other streams) never share scratch and a block is never reused while
+    kernels of an earlier call on another stream may still touch it."""
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
 def release():
-    with _ws_lock:
-        _workspaces.clear()
     if _lib.loaded():
         _lib.lib().cs_host_release()
 
@@ -105,8 +96,8 @@ def default_chunk(p, n, h, w):
 def _depth_geometry(p, depth, n, h, w, resize_depth):
     """Checks the depth batch against the image batch.  Frames of another size are an error for the function
     API (SIG:1586) and are resized on the GPU for the node (GS:141-148, GS:214-220): returns the params to use."""
-    if depth.shape[0] != n:
-        raise AssertionError('Depthmap and the image must have the same number of frames')
+    if depth.shape[0] != n:   # (callers cut a longer depth batch first: the reference only ever indexes depth_map[i], i < n)
+        raise IndexError(f'index {depth.shape[0]} is out of bounds for dimension 0 with size {depth.shape[0]}')
     if tuple(depth.shape[1:3]) == (h, w):
         return p
     if not resize_depth:
@@ -133,6 +124,7 @@ def stereo_batch_device(image, depth, p, out=None, chunk=None, resize_depth=Fals
         raise ValueError("image must have 3 channels")
     if depth.dim() == 3:
         depth = depth.unsqueeze(-1)
+    depth = depth[:n]
     p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     lib = _lib.lib()
@@ -170,9 +162,10 @@ def _out_bytes(s_shape, d_shape, m_shape):
     return total
 
 
-def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=False):
+def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=False, progress=None):
     """The hot path on CPU tensors (what ComfyUI hands the node): chunks are streamed through the
-    GPU with upload, kernels and download overlapped inside the library.  Returns CPU tensors."""
+    GPU with upload, kernels and download overlapped inside the library.  Returns CPU tensors.
+    progress(frames), if given, is called on this thread each time another chunk of frames is complete (GS:173, GS:262)."""
     if image.is_cuda or depth.is_cuda:
         raise ValueError("stereo_batch_host needs CPU tensors")
     image = image.contiguous().float()
@@ -182,6 +175,7 @@ def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=
         raise ValueError("image must have 3 channels")
     if depth.dim() == 3:
         depth = depth.unsqueeze(-1)
+    depth = depth[:n]
     p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
@@ -190,9 +184,10 @@ def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=
     dl = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
     dr = torch.empty(d_shape, dtype=torch.float32, pin_memory=pin)
     mask = torch.empty(m_shape, dtype=torch.float32, pin_memory=pin)
-    _lib.check(_lib.lib().cs_stereo_batch_host(ctypes.byref(p), image.data_ptr(), depth.data_ptr(), n, h, w, c,
-                                               stereo.data_ptr(), dl.data_ptr(), dr.data_ptr(), mask.data_ptr(),
-                                               int(device)))
+    cb = _lib.PROGRESS_FN(lambda frames, _user: progress(int(frames))) if progress is not None else None
+    _lib.check(_lib.lib().cs_stereo_batch_host_progress(ctypes.byref(p), image.data_ptr(), depth.data_ptr(), n, h, w, c,
+                                                        stereo.data_ptr(), dl.data_ptr(), dr.data_ptr(), mask.data_ptr(),
+                                                        int(device), ctypes.cast(cb, ctypes.c_void_p) if cb else None, None))
     return stereo, dl, dr, mask
 
 
@@ -212,7 +207,7 @@ def group_aligned_shard_range(n, rank, world, group):
     return min(glo * group, n), min(ghi * group, n)
 
 
-def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False):
+def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False, progress=None):
     """Frame-sharded run over several GPUs of one box from ONE process (used by the node when more
     than one device is visible).  No collective: every device streams its contiguous frame range
     and writes straight into its slice of the (pinned) host outputs, which is in-order assembly by
@@ -221,7 +216,7 @@ def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False):
     if depth.dim() == 3:
         depth = depth.unsqueeze(-1)
     image = image.contiguous().float()
-    depth = depth.contiguous().float()
+    depth = depth[:n].contiguous().float()
     p = _depth_geometry(p, depth, n, h, w, resize_depth)
     c = depth.shape[3]
     s_shape, d_shape, m_shape = output_shapes(p, n, h, w)
@@ -233,24 +228,43 @@ def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False):
     group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
     lib = _lib.lib()
     errors = []
+    done = [0]          # frames finished on any device; the caller's thread forwards it to `progress`
+    done_lock = threading.Lock()
+
+    def count(frames, _user):
+        with done_lock:
+            done[0] += int(frames)
+
+    cb = _lib.PROGRESS_FN(count)
 
     def work(rank, dev):
         lo, hi = group_aligned_shard_range(n, rank, len(devices), group)
         if hi <= lo:
             return
         try:
-            _lib.check(lib.cs_stereo_batch_host(
+            _lib.check(lib.cs_stereo_batch_host_progress(
                 ctypes.byref(p), image[lo:hi].data_ptr(), depth[lo:hi].data_ptr(), hi - lo, h, w, c,
                 outs[0][lo:hi].data_ptr(), outs[1][lo:hi].data_ptr(), outs[2][lo:hi].data_ptr(),
-                outs[3][lo:hi].data_ptr(), int(dev)))
+                outs[3][lo:hi].data_ptr(), int(dev), ctypes.cast(cb, ctypes.c_void_p), None))
         except Exception as e:  # noqa: BLE001 - re-raised on the caller's thread
             errors.append(e)
 
     threads = [threading.Thread(target=work, args=(r, d)) for r, d in enumerate(devices)]
     for t in threads:
         t.start()
+    reported = 0
+    while any(t.is_alive() for t in threads):     # the progress bar is only ever touched from the caller's thread
+        threads[0].join(timeout=0.02)
+        if progress is not None:
+            with done_lock:
+                now = done[0]
+            if now > reported:
+                progress(now - reported)
+                reported = now
     for t in threads:
         t.join()
+    if progress is not None and done[0] > reported:
+        progress(done[0] - reported)
     if errors:
         raise errors[0]
     return outs

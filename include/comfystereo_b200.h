@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 2
+#define CS_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CS_API __attribute__((visibility("default")))
@@ -183,6 +183,14 @@ CS_API int cs_stereo_batch(const cs_params *p, const float *image, const float *
 CS_API int cs_stereo_batch_host(const cs_params *p, const float *image, const float *depth, int n,
                          int h, int w, int c, float *stereo, float *depth_l, float *depth_r,
                          float *mask, int device);
+
+/* Same, reporting progress: `progress(frames, user)` is called on the calling thread, in frame order, each time
+ * another chunk of `frames` frames is complete in the caller's output buffers.  Replaces the reference's
+ * pbar.update(actual_batch_size) per sub-batch (GS:173) and pbar.update(1) per frame (GS:262); progress may be NULL. */
+typedef void (*cs_progress_fn)(int frames, void *user);
+CS_API int cs_stereo_batch_host_progress(const cs_params *p, const float *image, const float *depth, int n,
+                                  int h, int w, int c, float *stereo, float *depth_l, float *depth_r,
+                                  float *mask, int device, cs_progress_fn progress, void *user);
 
 /* Frees the device buffers / streams cs_stereo_batch_host caches between calls. */
 CS_API void cs_host_release(void);

@@ -171,11 +171,37 @@ def test_ragged_sizes_against_oracle(node, oracle, shape, fill):
                 assert np.array_equal(got[3], want[3])
 
 
-def test_one_process_multi_gpu_sharding(node, oracle):
-    """Inside ComfyUI there is one process: the node shards the batch frame-wise over every visible GPU (one host
-    thread and one pipeline per device, no collective) and assembles in order.  Needs >= 2 GPUs."""
+def test_progress_is_reported_per_chunk_and_depth_batch_may_be_longer(node, oracle, monkeypatch):
+    """GS:173 / GS:262: the reference moves its progress bar per sub-batch / per frame; the node reports every chunk of
+    frames as its results land (in order, on the calling thread) and the updates add up to the batch size.  A depth
+    batch longer than the image batch is simply not read beyond the images (the reference indexes depth_map[i])."""
+    import comfystereo_b200.GenerateStereo as gs
+    updates = []
+
+    class Bar:
+        def __init__(self, total):
+            self.total = total
+
+        def update(self, k):
+            updates.append(int(k))
+
+    monkeypatch.setattr(gs, "ProgressBar", Bar)
+    n = 5
+    img = syn.make_image(n, 1080, 1920, seed=3)        # 1080p: the host path moves one frame per chunk
+    dep = syn.make_depth(n + 2, 1080, 1920, "scene", seed=3)
+    got, p = run(node, img, dep, fill_technique="Fill - Naive", divergence=3.0)
+    assert sum(updates) == n and len(updates) >= 2 and all(u > 0 for u in updates), updates
+    want = oracle.node_generate(img[:1], dep[:1], **p)
+    assert np.array_equal(q8(got[0][:1]), q8(want[0]))
+    assert got[0].shape[0] == n
+
+
+def test_one_process_multi_gpu_sharding(node, oracle, monkeypatch):
+    """Inside ComfyUI there is one process: with COMFYSTEREO_MULTI_GPU=1 the node shards the batch frame-wise over every
+    visible GPU (one host thread and one pipeline per device, no collective) and assembles in order.  Needs >= 2 GPUs."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
+    monkeypatch.setenv("COMFYSTEREO_MULTI_GPU", "1")
     from comfystereo_b200 import engine
     n = 9
     img = syn.make_image(n, 270, 480, seed=71)
@@ -215,12 +241,45 @@ def test_very_wide_rows(oracle, fill):
         assert diff.max() <= (1 if fill == "hybrid_edge" else 0), (fill, w, int((diff > 0).sum()))
 
 
-@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 8000), ("Fill - Polylines Soft", 12000),
-                                       ("GPU Warp (Fast)", 9000), ("Fill - Naive", 16000),
+@pytest.mark.parametrize("fill,w", [("Fill - Polylines Sharp", 8192), ("Fill - Polylines Soft", 16384),
+                                    ("Fill - Polylines Sharp", 12288)])
+def test_polylines_wide_rows_are_tiled(oracle, fill, w):
+    """The reference has no width limit (SIG:1918-1947 allocates 5 + 2w points per row); Polylines rows of any width are cut
+    into tiles here.  8192 px (VR180 8K side by side) and 16384 px rows against the oracle, through the node."""
+    from comfystereo_b200 import StereoImageNode
+    node = StereoImageNode()
+    kw = dict(divergence=3.0, separation=0.5, modes="left-right", stereo_balance=0.3, convergence_point=0.5,
+              stereo_offset_exponent=2.0, fill_technique=fill, depth_blur_edge_threshold=20.0, depth_blur_strength=12.0,
+              depth_map_blur=True, depth_blur_falloff=2.0, depth_blur_vert_smooth=3, batch_size=2)
+    h = 6
+    img = syn.make_image(1, h, w, seed=11)
+    dep = syn.make_depth(1, h, w, "scene", seed=11, channels=1)
+    got = [o.numpy() for o in node.generate(torch.from_numpy(img), torch.from_numpy(dep), **kw)]
+    want = oracle.node_generate(img, dep, **kw)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(q8(g), q8(w_))
+
+
+def test_polylines_sequential_fallback_with_global_tables(oracle):
+    """Rows too wide for the sequential kernel's shared-memory tables (the fallback for rows whose list replay gives up)
+    keep them in global scratch: forced here for every row of a 9000 px image, against the oracle."""
+    import gpu_util as gu
+    rng = np.random.default_rng(5)
+    h, w = 3, 9000
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    d = (syn.make_depth(1, h, w, "quant", seed=5, channels=1)[0, ..., 0] * np.float32(255)).astype(np.float32)
+    for fill in ("polylines_sharp", "polylines_soft"):
+        got = gu.warp_fill(img, d, fill, 2.5, 0.1, 2.0, 0.5, exact=True)[..., :3]
+        want = oracle.apply_stereo_divergence(img, d, 2.5, 0.1, 2.0, fill, 0.5)
+        assert np.array_equal(got, want), fill
+
+
+@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 32766), ("GPU Warp (Fast)", 9000), ("Fill - Naive", 16000),
                                        ("Imperfect fill - Hybrid Edge", 16000)])
 def test_row_capacity_limits(oracle, fill, wmax):
-    """One row (or tile) lives in a CTA's shared memory, so every technique has a documented maximum width: at the limit
-    the node still matches the oracle, one step beyond it the library refuses up front (CS_ERR_UNSUPPORTED)."""
+    """The row techniques keep one row per CTA in shared memory and have a documented maximum width; Polylines is bounded
+    only by the 16-bit point indices of its sequential fallback (32766 px sharp, 65533 px soft).  At the limit the node
+    still matches the oracle, one step beyond it the library refuses up front (CS_ERR_UNSUPPORTED)."""
     from comfystereo_b200 import StereoImageNode
     from comfystereo_b200._lib import CsError
     node = StereoImageNode()

@@ -13,6 +13,9 @@ Tolerances (the bar BASELINE.json's north_star sets):
     hard part 2); those are counted and bounded (<= 0.5 % of pixels off by more than 1 LSB), depth outputs
     are held to 1 LSB circular (wrap quirk Q1)
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -23,6 +26,8 @@ from comfystereo_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 MAN = load_manifest()
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "node_flip_counts.json")) as _f:
+    FLIPS = json.load(_f)   # per node fixture: output pixels the blur's float32 rounding moves (measure_node_flips.py)
 STAGE = {k: [s for s in MAN["stage"] if s["stage"] == k] for k in ("blur", "warp", "gpuwarp")}
 
 
@@ -216,14 +221,14 @@ def test_node_vs_oracle_and_reference(gu, oracle, node, spec):
     o_st, o_dl, o_dr, o_mk = oracle.node_generate(img, dep, **params)
     fill = params["fill_technique"]
     blur_on = "blur_l" in g.files
-    # Depth with exact plateaus (flat / steps / card / quant) + blur: inside a plateau the blurred value is
-    # "the plateau +- float32 summation noise", and min/max normalisation or a z-test between equal levels turns
-    # that noise into whole-pixel decisions.  Those pixels follow the rounding of whichever conv2d produced the
-    # blur, so the end-to-end comparison with the reference's fixture is only meaningful on continuous depth;
-    # plateau classes are held to the bar stage-wise, with the reference's own blurred depth injected
-    # (test_stagewise_with_reference_blur / test_forward_warp_with_reference_blur).
-    chaotic = blur_on and spec["kind"] in ("flat", "steps", "card", "quant")
-    lim = 5e-3
+    # End to end against the reference's own output, blur included.  The blurred depth is the only thing that can
+    # differ (torch's conv2d summation order is unspecified: <= 2e-4 on the 0..255 scale, pinned by the blur stage
+    # tests; with the reference's blurred depth injected everything downstream is bit-exact,
+    # test_stagewise_with_reference_blur).  How many output pixels that noise moves is MEASURED per fixture
+    # (oracle/measure_node_flips.py -> tests/golden/node_flip_counts.json): zero on every continuous-depth fixture; on
+    # depth with exact plateaus (flat / steps / card / quant) min/max normalisation or a z-test between equal levels
+    # turns the noise into a fixed, recorded number of whole-pixel decisions.  Each fixture is held to its own count.
+    flips = FLIPS.get(spec["name"], {"pixels": 0, "mask": 0})
     assert stereo.shape == o_st.shape and dl.shape == o_dl.shape and mask.shape == o_mk.shape
     assert stereo.dtype == np.float32 and mask.dtype == np.float32
     if fill == 'GPU Warp (Fast)':
@@ -234,12 +239,11 @@ def test_node_vs_oracle_and_reference(gu, oracle, node, spec):
         assert np.abs(stereo - o_st).max() <= (1e-6 if special else 1e-5)
         # (b) reference
         assert np.abs(dl[..., 0] - g["depth_l"]).max() <= 1e-6 and np.abs(dr[..., 0] - g["depth_r"]).max() <= 1e-6
-        bad_mask = ((mask > 0).astype(np.uint8) != g["mask"]).mean()
-        bad_px = (np.abs(stereo - g["stereo"]).max(axis=-1) > 1.0 / 255).mean()
-        if chaotic:
-            pass
-        elif blur_on:
-            assert bad_mask <= lim and bad_px <= lim, (bad_mask, bad_px)
+        bad_mask = int(((mask > 0).astype(np.uint8) != g["mask"]).sum())
+        bad_px = int((np.abs(stereo - g["stereo"]).max(axis=-1) > 1.0 / 255).sum())
+        if blur_on:
+            # (float image: a pixel exactly at the 1/255 threshold may fall either side of it -> slack of 2)
+            assert bad_mask == flips["mask"] and abs(bad_px - flips["pixels"]) <= 2, (bad_mask, bad_px, flips)
         else:
             assert bad_mask == 0 and np.abs(stereo - g["stereo"]).max() <= 2e-5
     else:
@@ -254,12 +258,12 @@ def test_node_vs_oracle_and_reference(gu, oracle, node, spec):
         # (b) reference
         assert circ_dist_u8(q(dl[..., 0]), g["depth_l"]).max() <= 1
         assert circ_dist_u8(q(dr[..., 0]), g["depth_r"]).max() <= 1
-        bad_px = (np.abs(q(stereo).astype(np.int32) - g["stereo"].astype(np.int32)).max(axis=-1) > 1).mean()
-        bad_mask = (q(mask) != g["mask"]).mean()
-        if chaotic:
-            pass
-        elif blur_on:
-            assert bad_px <= lim and bad_mask <= lim, (bad_px, bad_mask)
+        bad_px = int((np.abs(q(stereo).astype(np.int32) - g["stereo"].astype(np.int32)).max(axis=-1) > 1).sum())
+        bad_mask = int((q(mask) != g["mask"]).sum())
+        if blur_on and 'Hybrid' not in fill:
+            assert bad_px == flips["pixels"] and bad_mask == flips["mask"], (bad_px, bad_mask, flips)
+        elif blur_on:   # Hybrid Edge colours are within 1 LSB of the oracle's (exp): a pixel 1 LSB off the reference may move
+            assert abs(bad_px - flips["pixels"]) <= 2 and bad_mask == flips["mask"], (bad_px, bad_mask, flips)
         else:
             assert bad_px == 0 and bad_mask == 0, (bad_px, bad_mask)
 

@@ -9,6 +9,9 @@ Tolerances (stated once, used everywhere):
     SURVEY.md section 8) every output is bit-exact; the oracle's own blur is held to 1 LSB on
     the (wrapping, quirk Q1) depth outputs.
 """
+import json
+import os
+import sys
 import zlib
 
 import numpy as np
@@ -107,6 +110,17 @@ def test_node_vs_reference(oracle, spec):
         assert np.array_equal(q(mask), g["mask"])
     if override is not None:  # the oracle's own blur, same inputs, float tolerance
         own = oracle.node_generate(img, dep, **spec["params"])
+        # ... and end to end: exactly the measured number of pixels the blur's rounding noise moves (0 on continuous depth)
+        sys_path_oracle = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+        if sys_path_oracle not in sys.path:
+            sys.path.insert(0, sys_path_oracle)
+        from measure_node_flips import flips as count_flips
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "node_flip_counts.json")) as f:
+            rec = json.load(f)[spec["name"]]
+        px, mk = count_flips(spec, g, own[0], own[3])
+        assert (px, mk) == (rec["pixels"], rec["mask"]), (px, mk, rec)
+        if spec["kind"] in ("scene", "noise"):
+            assert px == 0 and mk == 0
         if is_gw:
             assert np.abs(own[1][..., 0] - g["depth_l"]).max() <= 1e-6
             assert np.abs(own[2][..., 0] - g["depth_r"]).max() <= 1e-6

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--no-blur", action="store_true")
     ap.add_argument("--kind", default="scene")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--chunk", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -41,18 +42,18 @@ def main():
     img_d, dep_d = torch.from_numpy(img).to(dev), torch.from_numpy(dep).to(dev)
     outs = engine.stereo_batch_device(img_d, dep_d, p)
     for _ in range(3):
-        engine.stereo_batch_device(img_d, dep_d, p, out=outs)
+        engine.stereo_batch_device(img_d, dep_d, p, out=outs, chunk=(a.chunk or None))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        engine.stereo_batch_device(img_d, dep_d, p, out=outs)
+        engine.stereo_batch_device(img_d, dep_d, p, out=outs, chunk=(a.chunk or None))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     lib.cs_profile_enable(1)
     for _ in range(a.steps):
-        engine.stereo_batch_device(img_d, dep_d, p, out=outs)
+        engine.stereo_batch_device(img_d, dep_d, p, out=outs, chunk=(a.chunk or None))
     torch.cuda.synchronize()
     lib.cs_profile_enable(0)
     nk = lib.cs_profile_kernel_count()
