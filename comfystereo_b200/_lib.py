@@ -30,7 +30,7 @@ class CsParams(ctypes.Structure):
         ("blur_radius", ctypes.c_int32), ("blur_vert_smooth", ctypes.c_int32),
         ("blur_edge_threshold", ctypes.c_double), ("blur_falloff", ctypes.c_double),
         ("group_size", ctypes.c_int32), ("depth_h", ctypes.c_int32), ("depth_w", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("blur_flavor", ctypes.c_int32),
     ]
 
 

@@ -64,6 +64,7 @@ static int check_params(const cs_params* p) {
     if (p->mode < CS_MODE_LEFT_RIGHT || p->mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
     if (p->depth_h < 0 || p->depth_w < 0 || (p->depth_h > 0) != (p->depth_w > 0))
         return fail(CS_ERR_ARG, "depth_h/depth_w must both be 0 or both be positive");
+    if (p->blur_flavor != 0 && p->blur_flavor != 1) return fail(CS_ERR_ARG, "unknown blur_flavor %d", p->blur_flavor);
     if (p->blur_enabled) {
         if (p->blur_box < 1) return fail(CS_ERR_UNSUPPORTED, "kernel size should be greater than zero");
         if (p->blur_radius < 0 || p->blur_radius > kMaxBlurRadius)
@@ -431,6 +432,9 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     if (!image || !depth || !stereo || !depth_l || !depth_r || !mask || !workspace)
         return fail(CS_ERR_ARG, "cs_stereo_batch: NULL pointer");
     if (n < 1 || h < 1 || w < 2 || c < 1) return fail(CS_ERR_ARG, "cs_stereo_batch: bad size n=%d h=%d w=%d c=%d", n, h, w, c);
+    if (p->blur_flavor != 0)
+        return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: blur_flavor 1 (the scipy blur of non-tensor inputs) is a cs_blur option; "
+                    "the node's path always uses the torch blur");
     if ((uintptr_t)workspace % 256) return fail(CS_ERR_ARG, "cs_stereo_batch: workspace must be 256-byte aligned");
     const bool cpu = is_cpu_technique(p->fill);
     if (cpu && c != 1 && c != 3) return fail(CS_ERR_ARG, "cs_stereo_batch: depth must have 1 or 3 channels");

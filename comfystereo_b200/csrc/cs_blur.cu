@@ -41,6 +41,23 @@ __device__ __forceinline__ float scaled(float g, float scale) {
 }
 
 // ------------------------------------------------------------------------------------ dist
+// NP = true: scipy.ndimage.sobel as the reference's numpy blur calls it (SIG:1377): borders reflected (d c b a | a b c d),
+// derivative pass rounded to float32, then the [1 2 1] smoothing pass summed in float64 (centre first) and rounded.
+__device__ __forceinline__ float sobel_np(const float* __restrict__ base, int h, int w, int y, int x) {
+    const int xm = max(x - 1, 0), xp = min(x + 1, w - 1);
+    const int ym = max(y - 1, 0), yp = min(y + 1, h - 1);
+    const float* r0 = base + (int64_t)ym * w;
+    const float* r1 = base + (int64_t)y * w;
+    const float* r2 = base + (int64_t)yp * w;
+    const float g0 = (float)((double)r0[xp] - (double)r0[xm]);
+    const float g1 = (float)((double)r1[xp] - (double)r1[xm]);
+    const float g2 = (float)((double)r2[xp] - (double)r2[xm]);
+    double t = (double)g1 * 2.0;
+    t = t + ((double)g0 + (double)g2) * 1.0;
+    return (float)t;
+}
+
+template <bool NP>
 __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gray,
                                                    const FrameStats* __restrict__ st, int scale_mode,
                                                    int group, int n, int h, int w, float edge_div,
@@ -60,7 +77,15 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
     const int wpad = nwords << 5;
     for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
         bool ml = false, mr = false;
-        if (x < w) {
+        if (NP) {
+            if (x < w) {
+                const float g = sobel_np(base, h, w, y, x);
+                float e = fabsf(g) / edge_div;
+                e = fminf(fmaxf(e, 0.0f), 1.0f);
+                ml = (g > 0.0f) && (e > 0.5f);
+                mr = (g < 0.0f) && (e > 0.5f);
+            }
+        } else if (x < w) {
             float g = 0.0f;
             const bool hasl = x > 0, hasr = x + 1 < w;
             if (r0) {
@@ -366,6 +391,68 @@ __global__ void __launch_bounds__(kSeg, 4) k_blur_blend(
     }
 }
 
+// The numpy / scipy blur (SIG:1397-1419), one thread per pixel.  Not on the node's path (non-tensor inputs of
+// create_stereoimages only), so it is written for fidelity, not speed:
+//   weights  LUT(dist), then scipy's convolve1d over rows with nearest borders: float64, centre first, pairs from the
+//            outside in, rounded to float32, clipped to [0, 1]
+//   box      convolve1d along the row, nearest borders; an even box reaches bs/2 - 1 samples left and bs/2 right of the
+//            pixel; odd boxes are summed in the paired order, even ones last tap first and then ascending (NI_Correlate1D)
+__global__ void __launch_bounds__(256) k_blur_blend_np(const float* __restrict__ gray, FrameStats* __restrict__ st, int h, int w,
+                                                       int bs, int v, const __grid_constant__ BlurLut lut,
+                                                       const uint8_t* __restrict__ dist_l, const uint8_t* __restrict__ dist_r,
+                                                       float* __restrict__ blur_l, float* __restrict__ blur_r) {
+    const int frame = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    float vl = 0.0f, vr = 0.0f;
+    const bool in = x < w;
+    if (in) {
+        const float* base = gray + (int64_t)frame * h * w;
+        const uint8_t* dl = dist_l + (int64_t)frame * h * w;
+        const uint8_t* dr = dist_r + (int64_t)frame * h * w;
+        float wl, wr;
+        if (v > 0) {
+            const double k = 1.0 / (double)(2 * v + 1);
+            double al = (double)lut.w[dl[(int64_t)y * w + x]] * k, ar = (double)lut.w[dr[(int64_t)y * w + x]] * k;
+            for (int q = v; q >= 1; --q) {
+                const int ya = max(y - q, 0), yb = min(y + q, h - 1);
+                al = al + ((double)lut.w[dl[(int64_t)ya * w + x]] + (double)lut.w[dl[(int64_t)yb * w + x]]) * k;
+                ar = ar + ((double)lut.w[dr[(int64_t)ya * w + x]] + (double)lut.w[dr[(int64_t)yb * w + x]]) * k;
+            }
+            wl = fminf(fmaxf((float)al, 0.0f), 1.0f);
+            wr = fminf(fmaxf((float)ar, 0.0f), 1.0f);
+        } else {
+            wl = lut.w[dl[(int64_t)y * w + x]];
+            wr = lut.w[dr[(int64_t)y * w + x]];
+        }
+        const float* row = base + (int64_t)y * w;
+        const double kb = 1.0 / (double)bs;
+        double acc;
+        if (bs & 1) {
+            const int half = bs / 2;
+            acc = (double)row[x] * kb;
+            for (int q = half; q >= 1; --q)
+                acc = acc + ((double)row[max(x - q, 0)] + (double)row[min(x + q, w - 1)]) * kb;
+        } else {
+            const int lo = bs / 2 - 1;     // taps x - lo .. x + bs / 2
+            acc = (double)row[min(x + bs / 2, w - 1)] * kb;
+            for (int i = 0; i < bs - 1; ++i)
+                acc = acc + (double)row[min(max(x - lo + i, 0), w - 1)] * kb;
+        }
+        const float b = (float)acc, d = row[x];
+        float t0 = wl * b, t1 = (1.0f - wl) * d;
+        vl = t0 + t1;
+        t0 = wr * b; t1 = (1.0f - wr) * d;
+        vr = t0 + t1;
+        blur_l[((int64_t)frame * h + y) * w + x] = vl;
+        blur_r[((int64_t)frame * h + y) * w + x] = vr;
+    }
+    float mnl = in ? vl : INFINITY, mxl = in ? vl : -INFINITY, mnr = in ? vr : INFINITY, mxr = in ? vr : -INFINITY;
+    mnl = warp_min(mnl); mxl = warp_max(mxl); mnr = warp_min(mnr); mxr = warp_max(mxr);
+    if ((threadIdx.x & 31) == 0 && mnl <= mxl) {
+        atomicMin(&st[frame].l_min, f2ord(mnl)); atomicMax(&st[frame].l_max, f2ord(mxl));
+        atomicMin(&st[frame].r_min, f2ord(mnr)); atomicMax(&st[frame].r_max, f2ord(mxr));
+    }
+}
+
 // weight(dist) = clamp(1 - dist/R, 0, 1) ** falloff, float32 (SIG:1168).  Built on the host once
 // per call (<= 256 entries): torch.pow special-cases exponents 1, 2, 3, 0.5; otherwise powf.
 template <int V, typename... Args>
@@ -421,9 +508,15 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     uint8_t* dist_r = dist + (int64_t)n * h * w;
     const float edge_div = (float)(10.0 * p.blur_edge_threshold);  // python float 10*thr -> float32 scalar
     const int nwords = (w + 31) >> 5;
+    const bool np_flavor = p.blur_flavor == 1;
+    if (np_flavor && (scale_mode != 0 || depth_l_out || depth_r_out)) return cudaErrorInvalidValue;   // function-level only
     prof_begin(K_EDGE_DIST, s);
-    k_edge_dist<<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
-        gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
+    if (np_flavor)
+        k_edge_dist<true><<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
+            gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
+    else
+        k_edge_dist<false><<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
+            gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
     prof_end(K_EDGE_DIST, s);
     count_launch();
     cudaError_t e = cudaGetLastError();
@@ -431,6 +524,13 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
 
     BlurLut lut;
     build_lut(lut, radius, (float)p.blur_falloff);
+    if (np_flavor) {
+        prof_begin(K_BLUR_BLEND, s);
+        k_blur_blend_np<<<dim3((w + 255) / 256, h, n), 256, 0, s>>>(gray, stats, h, w, bs, v, lut, dist_l, dist_r, blur_l, blur_r);
+        prof_end(K_BLUR_BLEND, s);
+        count_launch();
+        return cudaGetLastError();
+    }
     const int segs = (w + kSeg - 1) / kSeg;
     const int tiles_y = (h + kTileY - 1) / kTileY;
     const int items = segs * tiles_y;

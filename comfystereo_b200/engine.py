@@ -84,11 +84,12 @@ def _stream_ptr(device):
 
 
 def default_chunk(p, n, h, w):
-    """Frames per kernel sequence: about four 1080p frames' worth of pixels.  Measured on B200 (chunk sweep in
-    profiles/): larger grids (fewer partial waves) matter more than keeping the ~26 B/px of scratch inside L2."""
+    """Frames per kernel sequence: about sixteen 1080p frames' worth of pixels.  Measured on B200 (chunk sweep in
+    profiles/): fewer, larger launches (fewer partial waves and launch gaps) matter more than keeping the ~26 B/px of
+    scratch inside L2 -- 4 / 8 / 16 frames per sequence: 3.73 / 3.56 / 3.46 ms per 16 frames of 1080p Polylines Sharp."""
     group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
     group = min(group, n)
-    target = max(1, int(8.4e6 // (h * w)))
+    target = max(1, int(33.6e6 // (h * w)))
     chunk = max(group, (target // group) * group)
     return min(chunk, n)
 
@@ -189,6 +190,53 @@ def stereo_batch_host(image, depth, p, device=0, pin_outputs=True, resize_depth=
                                                         stereo.data_ptr(), dl.data_ptr(), dr.data_ptr(), mask.data_ptr(),
                                                         int(device), ctypes.cast(cb, ctypes.c_void_p) if cb else None, None))
     return stereo, dl, dr, mask
+
+
+# ----------------------------------------------------------------------------------- stage calls (device tensors)
+def blur_device(depth, strength, edge_threshold, falloff=1.0, vert_smooth=0, flavor=0):
+    """cs_blur on a [n,h,w] float32 CUDA tensor: (left, right).  flavor 1 = the scipy blur of the reference's non-tensor
+    branch (SIG:1346-1419), 0 = the torch blur the node runs (SIG:1171-1251)."""
+    d = depth.contiguous()
+    n, h, w = d.shape
+    p = make_params('none', 'left-right', 1.0, depth_blur=True, depth_blur_strength=strength,
+                    depth_blur_edge_threshold=edge_threshold, depth_blur_falloff=falloff,
+                    depth_blur_vert_smooth=vert_smooth)
+    p.blur_flavor = int(flavor)
+    left, right = torch.empty_like(d), torch.empty_like(d)
+    scratch = torch.empty(2 * n * h * w, dtype=torch.uint8, device=d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.lib().cs_blur(d.data_ptr(), n, h, w, ctypes.byref(p), left.data_ptr(), right.data_ptr(), None,
+                                      scratch.data_ptr(), _stream_ptr(d.device)))
+    return left, right
+
+
+def warp_fill_device(image_rgbx, depth, fill_key, divergence, separation, exponent, convergence):
+    """cs_warp_fill (apply_stereo_divergence, SIG:1576-1620) for ONE eye: image_rgbx [n,h,w,4] uint8 CUDA, depth [n,h,w]
+    float32 as given.  Returns [n,h,w,4] uint8."""
+    n, h, w = depth.shape
+    out = torch.empty_like(image_rgbx)
+    lib = _lib.lib()
+    nb = lib.cs_warp_fill_scratch_bytes(n, h, w)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=depth.device)
+    with torch.cuda.device(depth.device):
+        _lib.check(lib.cs_warp_fill(image_rgbx.contiguous().data_ptr(), depth.contiguous().data_ptr(), n, h, w,
+                                    FILL_KEYS.index(fill_key), float(divergence), float(separation), float(exponent),
+                                    float(convergence), out.data_ptr(), scratch.data_ptr(), nb, _stream_ptr(depth.device)))
+    return out
+
+
+def compose_device(left_rgbx, right_rgbx, mode):
+    """cs_compose: two [n,h,w,4] uint8 eyes -> (stereo [n,ho,wo,3] float32 = u8 / 255, mask [n,ho,wo])."""
+    n, h, w, _ = left_rgbx.shape
+    m = MODES.index(mode)
+    ho, wo = (h, 2 * w) if m in (0, 1) else ((2 * h, w) if m in (2, 3) else (h, w))
+    dev = left_rgbx.device
+    stereo = torch.empty((n, ho, wo, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((n, ho, wo), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cs_compose(left_rgbx.contiguous().data_ptr(), right_rgbx.contiguous().data_ptr(), n, h, w, m,
+                                         stereo.data_ptr(), mask.data_ptr(), _stream_ptr(dev)))
+    return stereo, mask
 
 
 # ----------------------------------------------------------------------------------- sharding

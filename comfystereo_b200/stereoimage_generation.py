@@ -52,10 +52,10 @@ def create_stereoimages(original_image, depthmap, divergence, separation=0.0, mo
             raise Exception('Unknown mode')          # SIG:1562
     tensors = isinstance(depthmap, torch.Tensor) and isinstance(original_image, torch.Tensor)
     if not tensors:
-        raise NotImplementedError(
-            "non-tensor inputs select the reference's numpy branch (scipy blur SIG:1346-1419, no x255 "
-            "rescale), which the node never uses and which is outside the accelerated path; pass torch "
-            "tensors as the node does")
+        return _create_stereoimages_arrays(original_image, depthmap, divergence, separation, modes, stereo_balance,
+                                           stereo_offset_exponent, fill_technique, depth_blur_strength,
+                                           depth_blur_edge_threshold, direction_aware_depth_blur, return_modified_depth,
+                                           convergence_point, depth_blur_falloff, depth_blur_vert_smooth)
     dev = _device()
     img = original_image
     if img.dim() == 3 and img.shape[0] == 3 and img.shape[2] != 3:
@@ -91,6 +91,57 @@ def create_stereoimages(original_image, depthmap, divergence, separation=0.0, mo
     if direction_aware_depth_blur:
         return stereo_images, Image.fromarray(left_u8), Image.fromarray(right_u8)
     return stereo_images, Image.fromarray(left_u8)
+
+
+def _create_stereoimages_arrays(original_image, depthmap, divergence, separation, modes, stereo_balance,
+                                stereo_offset_exponent, fill_technique, depth_blur_strength, depth_blur_edge_threshold,
+                                direction_aware_depth_blur, return_modified_depth, convergence_point, depth_blur_falloff,
+                                depth_blur_vert_smooth):
+    """The reference's branch for NON-tensor inputs (numpy arrays, PIL images; SIG:1486-1496, 1520-1526): the image is
+    used as it is (uint8), the depth as it is (no x255 rescale), the blur is the scipy one (reflected Sobel, nearest-border
+    boxes: engine.blur_device(flavor=1)), and the depth outputs are trunc(clip(depth, 0, 255)).  The node never takes it."""
+    import numpy as np
+    from PIL import Image
+    img = np.asarray(original_image)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise NotImplementedError("non-tensor images must be uint8 [H,W,3] arrays or RGB PIL images")
+    depth = np.asarray(depthmap).astype(np.float32)
+    if depth.ndim != 2:
+        raise NotImplementedError("non-tensor depth maps must be [H,W]")
+    dev = _device()
+    d = torch.from_numpy(np.ascontiguousarray(depth)).to(dev).unsqueeze(0)
+    if direction_aware_depth_blur and depth_blur_strength > 0:
+        if int(round(float(depth_blur_strength))) <= 0:
+            raise RuntimeError("filter weights array has incorrect shape.")     # what scipy's convolve1d says
+        dl, dr = engine.blur_device(d, depth_blur_strength, depth_blur_edge_threshold, depth_blur_falloff,
+                                    depth_blur_vert_smooth, flavor=1)
+    else:
+        dl = dr = d
+    rgbx = torch.zeros(img.shape[:2] + (4,), dtype=torch.uint8)
+    rgbx[..., :3] = torch.from_numpy(np.ascontiguousarray(img))
+    rgbx = rgbx.to(dev).unsqueeze(0)
+    ldiv, rdiv = divergence * (1 + stereo_balance), divergence * (1 - stereo_balance)
+    known = fill_technique in _CPU_FILLS      # unknown keys: apply_stereo_divergence returns the image, SIG:1620
+    if known and (ldiv >= 0.001 or rdiv >= 0.001):
+        assert tuple(img.shape[:2]) == tuple(depth.shape), 'Depthmap and the image must have the same size'   # SIG:1586
+    left = rgbx if (ldiv < 0.001 or not known) else engine.warp_fill_device(
+        rgbx, dl, fill_technique, +1 * ldiv, -1 * separation, stereo_offset_exponent, convergence_point)
+    right = rgbx if (rdiv < 0.001 or not known) else engine.warp_fill_device(
+        rgbx, dr, fill_technique, -1 * rdiv, separation, stereo_offset_exponent, convergence_point)
+    results = []
+    for mode in modes:
+        stereo, _ = engine.compose_device(left, right, mode)
+        results.append(_float_to_u8(stereo[0]).cpu().numpy())
+    stereo_images = _to_pil_list(results)
+    if not return_modified_depth:
+        return stereo_images
+
+    def depth_image(t):
+        return Image.fromarray(t[0].clamp(0, 255).to(torch.uint8).cpu().numpy())    # np.clip(...).astype(uint8): truncation
+
+    if direction_aware_depth_blur:
+        return stereo_images, depth_image(dl), depth_image(dr)
+    return stereo_images, depth_image(d)
 
 
 def create_stereoimages_gpu(image_tensor, depth_tensor, divergence, separation=0.0, modes=None,

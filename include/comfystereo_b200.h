@@ -93,7 +93,9 @@ typedef struct cs_params {
                                    the "is depth 0..1 or 0..255" tests are sub-batch wide (SIG:1045, 315, 1125) */
     int32_t depth_h;            /* size of the depth frames when it differs from the image's (GS:141-148, GS:214-220): */
     int32_t depth_w;            /* the gray depth is resized bilinearly (align_corners=False) first; 0 = same as the image */
-    int32_t reserved;
+    int32_t blur_flavor;        /* 0: directional_motion_blur_gpu (torch, zero padding; what the node runs), SIG:1171-1251
+                                   1: directional_motion_blur (scipy: reflected Sobel, nearest-border float64 box sums), the
+                                      blur create_stereoimages applies to non-tensor inputs, SIG:1346-1419 */
 } cs_params;
 
 CS_API int cs_abi_version(void);

@@ -339,6 +339,54 @@ def main_dark():
     print("dark cases:", len(DARK_CASES))
 
 
+# ---- non-tensor inputs of create_stereoimages (numpy arrays / PIL images): SIG:1486-1496, scipy blur SIG:1346-1419 -------------
+ARRAY_CASES = [
+    dict(name="000", h=40, w=97, kind="scene", seed=1, fill="polylines_sharp", blur=True, s=20.0, thr=20.0, fo=2.0, v=6, div=8.0, sep=0.0, bal=0.0, expo=2.0, conv=0.5, modes=["left-right", "red-cyan-anaglyph"]),
+    dict(name="001", h=33, w=64, kind="steps", seed=2, fill="naive", blur=True, s=7.3, thr=6.0, fo=1.0, v=0, div=6.0, sep=1.0, bal=0.3, expo=1.0, conv=0.0, modes=["top-bottom"]),
+    dict(name="002", h=25, w=130, kind="noise", seed=3, fill="polylines_soft", blur=True, s=4.0, thr=2.0, fo=0.5, v=3, div=5.0, sep=-1.0, bal=-0.4, expo=2.0, conv=1.0, modes=["right-left"]),
+    dict(name="003", h=60, w=80, kind="card", seed=4, fill="inverse", blur=True, s=21.0, thr=30.0, fo=3.0, v=15, div=10.0, sep=0.0, bal=0.0, expo=2.0, conv=0.5, modes=["left-right"]),
+    dict(name="004", h=30, w=90, kind="quant", seed=5, fill="naive_interpolating", blur=False, s=0.0, thr=6.0, fo=1.0, v=0, div=7.0, sep=0.0, bal=0.0, expo=2.0, conv=0.5, modes=["bottom-top"]),
+    dict(name="005", h=24, w=70, kind="scene", seed=6, fill="hybrid_edge", blur=True, s=9.0, thr=10.0, fo=2.0, v=2, div=9.0, sep=0.5, bal=0.0, expo=2.0, conv=0.3, modes=["left-right"]),
+    dict(name="006", h=20, w=50, kind="scene", seed=7, fill="none", blur=True, s=33.0, thr=5.0, fo=2.0, v=2, div=4.0, sep=0.0, bal=0.95, expo=2.0, conv=0.5, modes=["left-right"]),
+]
+
+
+def array_inputs(spec):
+    """uint8 RGB image and a float32 depth map on the 0..255 scale (what a PIL 'L' depth image gives), from seeds."""
+    img = (syn.make_image(1, spec["h"], spec["w"], seed=spec["seed"])[0] * 255).astype(np.uint8)
+    d = (syn.make_depth(1, spec["h"], spec["w"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0] * np.float32(255))
+    return img, d.astype(np.float32)
+
+
+def main_arrays():
+    """python oracle/make_golden.py arrays -- create_stereoimages with numpy inputs, and the scipy blur on its own."""
+    assert ref_loader.reference_available(), "needs /root/reference"
+    sig = ref_loader.load_sig()
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    manifest["arrays"] = []
+    for spec in ARRAY_CASES:
+        img, d = array_inputs(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = sig.create_stereoimages(img.copy(), d.copy(), spec["div"], spec["sep"], list(spec["modes"]), spec["bal"], spec["expo"],
+                                          spec["fill"], spec["s"], spec["thr"], spec["blur"], True, spec["conv"], spec["fo"], spec["v"])
+            rec = dict(crc=crc(img, d))
+            for i, im in enumerate(out[0]):
+                rec[f"stereo{i}"] = np.asarray(im)
+            rec["depth_l"] = np.asarray(out[1])
+            if spec["blur"]:
+                rec["depth_r"] = np.asarray(out[2])
+                bl, br = sig.directional_motion_blur(d.copy(), spec["s"], spec["thr"], spec["s"], falloff_exponent=spec["fo"],
+                                                     vert_smooth_px=spec["v"])
+                rec["blur_l"], rec["blur_r"] = bl.astype(np.float32), br.astype(np.float32)
+        np.savez_compressed(os.path.join(GOLDEN, f"arrays_{spec['name']}.npz"), **rec)
+        manifest["arrays"].append(spec)
+        print("arrays", spec["name"], spec["fill"], flush=True)
+    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -378,5 +426,7 @@ if __name__ == "__main__":
         main_resize()
     elif len(sys.argv) > 1 and sys.argv[1] == "dark":
         main_dark()
+    elif len(sys.argv) > 1 and sys.argv[1] == "arrays":
+        main_arrays()
     else:
         main()

@@ -420,3 +420,105 @@ def node_generate(image, depth_map, divergence=4.5, separation=0.0, modes="left-
             black = (r.astype(np.int32).sum(axis=-1) == 0).astype(np.uint8) * 255  # GS:355-361 (Q6)
             ms.append((black.astype(np.float32) / f255)[None])
     return (np.concatenate(st), np.concatenate(dls), np.concatenate(drs), np.concatenate(ms))
+
+
+# ------------------------------------------------------------------ non-tensor inputs (numpy / PIL): SIG:1346-1419
+def _corr1d_f32(a, weights, axis, mode, origin=0):
+    """scipy.ndimage.correlate1d on a float32 array with float64 weights, restated: every output sample is a float64
+    sum over the (border-extended) line, rounded once to float32.  Odd symmetric / antisymmetric kernels take scipy's
+    paired form (centre first, then pairs from the outside in); other kernels start with the LAST tap and then add the
+    others in ascending order (NI_Correlate1D's general loop) -- the order matters: box sums of float32 samples hit exact
+    float32 rounding ties about once in a thousand."""
+    a = np.asarray(a, np.float32)
+    w = np.asarray(weights, np.float64)
+    n = len(w)
+    s1 = n // 2 + origin
+    s2 = n - n // 2 - 1 - origin
+    pad = [(0, 0)] * a.ndim
+    pad[axis] = (s1, s2)
+    ext = np.pad(a, pad, mode={'reflect': 'symmetric', 'nearest': 'edge'}[mode]).astype(np.float64)
+    L = a.shape[axis]
+
+    def tap(i):   # extended line shifted so that tap i lines up with the output sample
+        sl = [slice(None)] * a.ndim
+        sl[axis] = slice(i, i + L)
+        return ext[tuple(sl)]
+
+    half = n // 2
+    sym = (n & 1) and all(abs(w[half - k] - w[half + k]) <= np.finfo(np.float64).eps for k in range(1, half + 1))
+    asym = (n & 1) and all(abs(w[half - k] + w[half + k]) <= np.finfo(np.float64).eps for k in range(1, half + 1))
+    if sym or asym:
+        acc = tap(half) * w[half]
+        for k in range(half, 0, -1):          # ll = -size1 .. -1: outermost pair first
+            pair = (tap(half - k) + tap(half + k)) if sym else (tap(half + k) - tap(half - k))
+            acc = acc + pair * (w[half - k] if sym else w[half + k])
+    else:
+        acc = tap(n - 1) * w[n - 1]
+        for i in range(n - 1):
+            acc = acc + tap(i) * w[i]
+    return acc.astype(np.float32)
+
+
+def blur_numpy(depth, strength, edge_threshold, falloff=1.0, vert_smooth=0):
+    """directional_motion_blur(depth, s, thr, s, falloff, vert) -- the scipy blur the reference applies to NON-tensor
+    inputs (SIG:1346-1419): Sobel with reflected borders, nearest-border box filters (scipy's convolve1d: an even box
+    reaches one sample further right than left), float64 sums rounded to float32.  depth is used as given (no x255)."""
+    d = np.ascontiguousarray(depth, np.float32)
+    if strength <= 0:
+        return d, d
+    bs, R = py_round_half_even(strength), int(strength)
+    h, w = d.shape
+    g = _corr1d_f32(_corr1d_f32(d, [-1.0, 0.0, 1.0], 1, 'reflect'), [1.0, 2.0, 1.0], 0, 'reflect')   # scipy.ndimage.sobel
+    e = np.clip(np.abs(g) / np.float32(10 * edge_threshold), 0, 1)
+    masks = ((g > 0) & (e > 0.5), (g < 0) & (e > 0.5))
+    cols = np.arange(w, dtype=np.float32)
+    far = np.float32(R + 1)
+
+    def weight(mask):
+        last_l = np.maximum.accumulate(np.where(mask, cols[None, :], np.float32(-1)), axis=1)
+        dist_l = np.where(last_l >= 0, cols[None, :] - last_l, far)
+        last_r = np.maximum.accumulate(np.where(mask[:, ::-1], cols[None, :], np.float32(-1)), axis=1)
+        dist_r = np.where(last_r >= 0, cols[None, :] - last_r, far)[:, ::-1]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            wgt = np.clip(np.float32(1.0) - np.minimum(dist_l, dist_r) / np.float32(R), 0.0, 1.0) ** np.float32(falloff)
+        return wgt.astype(np.float32)
+
+    wl, wr = weight(masks[0]), weight(masks[1])
+    if vert_smooth > 0:
+        k = np.ones(2 * vert_smooth + 1) / (2 * vert_smooth + 1)
+        wl = np.clip(_corr1d_f32(wl, k, 0, 'nearest'), 0.0, 1.0)
+        wr = np.clip(_corr1d_f32(wr, k, 0, 'nearest'), 0.0, 1.0)
+    box = np.ones(bs) / bs
+    b = _corr1d_f32(d, box, 1, 'nearest', origin=(-1 if bs % 2 == 0 else 0))   # convolve1d: flipped box, origin - 1 if even
+    one = np.float32(1.0)
+    return (wl * b + (one - wl) * d).astype(np.float32), (wr * b + (one - wr) * d).astype(np.float32)
+
+
+def create_stereoimages_arrays(image_u8, depth, divergence, separation=0.0, modes=None, stereo_balance=0.0,
+                               stereo_offset_exponent=1.0, fill_technique='polylines_sharp', depth_blur_strength=0.0,
+                               depth_blur_edge_threshold=6.0, direction_aware_depth_blur=False, convergence_point=0.5,
+                               depth_blur_falloff=1.0, depth_blur_vert_smooth=0):
+    """Non-tensor branch of create_stereoimages (SIG:1486-1496, 1520-1574): uint8 image and float depth used as given,
+    scipy blur, depth outputs trunc(clip(depth, 0, 255)).  Returns (list of uint8 images, left depth u8, right depth u8)."""
+    if modes is None:
+        modes = ['left-right']
+    if not isinstance(modes, list):
+        modes = [modes]
+    img = np.ascontiguousarray(image_u8, np.uint8)
+    d = np.ascontiguousarray(depth, np.float32)
+    if direction_aware_depth_blur:
+        dl, dr = blur_numpy(d, depth_blur_strength, depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth)
+    else:
+        dl = dr = d
+    ldiv, rdiv = divergence * (1 + stereo_balance), divergence * (1 - stereo_balance)
+    left = img if ldiv < 0.001 else apply_stereo_divergence(
+        img, dl, +1 * ldiv, -1 * separation, stereo_offset_exponent, fill_technique, convergence_point)
+    right = img if rdiv < 0.001 else apply_stereo_divergence(
+        img, dr, -1 * rdiv, separation, stereo_offset_exponent, fill_technique, convergence_point)
+    results = []
+    for mode in modes:
+        if mode not in MODES:
+            raise Exception('Unknown mode')
+        results.append(compose_u8(left, right, mode))
+    q = lambda a: np.clip(a, 0, 255).astype(np.uint8)
+    return results, q(dl), q(dr)

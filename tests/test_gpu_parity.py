@@ -495,3 +495,38 @@ def test_polylines_small_coordinates_exact(gu, oracle, fill):
         nd = oracle.normalize(d, conv)
         want = oracle.polylines(img, nd, (div / 100.0) * w, (sep / 100.0) * w, expo, fill == "polylines_sharp")
         assert np.array_equal(got, want), f"{(got != want).any(axis=-1).sum()} pixels differ"
+
+
+def _array_inputs(spec):
+    img = (syn.make_image(1, spec["h"], spec["w"], seed=spec["seed"])[0] * 255).astype(np.uint8)
+    d = (syn.make_depth(1, spec["h"], spec["w"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0] * np.float32(255))
+    return img, d.astype(np.float32)
+
+
+@pytest.mark.parametrize("spec", MAN.get("arrays", []), ids=[s["name"] + "_" + s["fill"] for s in MAN.get("arrays", [])])
+def test_array_inputs_vs_reference(gu, oracle, spec):
+    """create_stereoimages with numpy / PIL inputs (SIG:1486-1496): the scipy-flavoured blur kernels (cs_params.blur_flavor
+    1) against the reference's own blurred depth (bit-exact for the special falloff exponents; powf otherwise) and every
+    returned image against the reference's."""
+    from PIL import Image
+    from comfystereo_b200 import stereoimage_generation as sig, engine
+    g = load_golden("arrays", spec["name"])
+    img, d = _array_inputs(spec)
+    if spec["blur"]:
+        bl, br = engine.blur_device(torch.from_numpy(d).cuda()[None], spec["s"], spec["thr"], spec["fo"], spec["v"], flavor=1)
+        special = spec["fo"] in (1.0, 2.0, 3.0, 0.5)
+        for got, want in ((bl, g["blur_l"]), (br, g["blur_r"])):
+            got = got[0].cpu().numpy()
+            if special:
+                assert np.array_equal(got, want, equal_nan=True)
+            else:
+                assert np.nanmax(np.abs(got - want)) <= 1e-4
+    # PIL image + numpy depth, as a script outside ComfyUI would call it
+    out = sig.create_stereoimages(Image.fromarray(img), d, spec["div"], spec["sep"], list(spec["modes"]), spec["bal"], spec["expo"],
+                                  spec["fill"], spec["s"], spec["thr"], spec["blur"], True, spec["conv"], spec["fo"], spec["v"])
+    for i, im in enumerate(out[0]):
+        diff = np.abs(np.asarray(im).astype(np.int32) - g[f"stereo{i}"].astype(np.int32))
+        assert diff.max() <= (1 if spec["fill"].startswith("hybrid") else 0), (i, int((diff > 0).sum()))
+    assert np.array_equal(np.asarray(out[1]), g["depth_l"])
+    if spec["blur"]:
+        assert np.array_equal(np.asarray(out[2]), g["depth_r"])

@@ -127,3 +127,30 @@ def test_node_vs_reference(oracle, spec):
         else:
             assert circ_dist_u8(q(own[1][..., 0]), g["depth_l"]).max() <= 1
             assert circ_dist_u8(q(own[2][..., 0]), g["depth_r"]).max() <= 1
+
+
+def _array_inputs(spec):
+    img = (syn.make_image(1, spec["h"], spec["w"], seed=spec["seed"])[0] * 255).astype(np.uint8)
+    d = (syn.make_depth(1, spec["h"], spec["w"], spec["kind"], seed=spec["seed"], channels=1)[0, ..., 0] * np.float32(255))
+    return img, d.astype(np.float32)
+
+
+@pytest.mark.parametrize("spec", MAN.get("arrays", []), ids=[s["name"] + "_" + s["fill"] for s in MAN.get("arrays", [])])
+def test_array_inputs_vs_reference(oracle, spec):
+    """create_stereoimages with NON-tensor inputs (numpy arrays / PIL, SIG:1486-1496): the scipy blur (reflected Sobel,
+    nearest-border float64 box sums in scipy's own order) is restated bit for bit, so every output is exact."""
+    g = load_golden("arrays", spec["name"])
+    img, d = _array_inputs(spec)
+    assert _crc(img, d) == int(g["crc"])
+    if spec["blur"]:
+        bl, br = oracle.blur_numpy(d, spec["s"], spec["thr"], spec["fo"], spec["v"])
+        assert np.array_equal(bl, g["blur_l"], equal_nan=True) and np.array_equal(br, g["blur_r"], equal_nan=True)
+    res, dl, dr = oracle.create_stereoimages_arrays(img, d, spec["div"], spec["sep"], list(spec["modes"]), spec["bal"], spec["expo"],
+                                                    spec["fill"], spec["s"], spec["thr"], spec["blur"], spec["conv"], spec["fo"],
+                                                    spec["v"])
+    for i, r in enumerate(res):
+        diff = np.abs(r.astype(np.int32) - g[f"stereo{i}"].astype(np.int32))
+        assert diff.max() <= (1 if spec["fill"].startswith("hybrid") else 0)
+    assert np.array_equal(dl, g["depth_l"])
+    if spec["blur"]:
+        assert np.array_equal(dr, g["depth_r"])
