@@ -482,7 +482,7 @@ static void launch_blend_v(int v, dim3 grid, size_t smem, cudaStream_t s, Args..
     }
 }
 
-static void build_lut(BlurLut& lut, int radius, float falloff) {
+static void build_lut(BlurLut& lut, int radius, float falloff, bool numpy_pow = false) {
     for (int k = 0; k < 256; ++k) {
         float q = (float)k / (float)radius;   // radius 0 -> NaN at k = 0, inf elsewhere (quirk Q11)
         float wgt = 1.0f - q;
@@ -491,7 +491,7 @@ static void build_lut(BlurLut& lut, int radius, float falloff) {
             if (wgt > 1.0f) wgt = 1.0f;
             if (falloff == 1.0f) {}
             else if (falloff == 2.0f) wgt = wgt * wgt;
-            else if (falloff == 3.0f) wgt = (wgt * wgt) * wgt;
+            else if (falloff == 3.0f && !numpy_pow) wgt = (wgt * wgt) * wgt;   // torch.pow only; numpy calls powf
             else if (falloff == 0.5f) wgt = sqrtf(wgt);
             else wgt = powf(wgt, falloff);
         }
@@ -523,7 +523,7 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     if (e != cudaSuccess) return e;
 
     BlurLut lut;
-    build_lut(lut, radius, (float)p.blur_falloff);
+    build_lut(lut, radius, (float)p.blur_falloff, np_flavor);
     if (np_flavor) {
         prof_begin(K_BLUR_BLEND, s);
         k_blur_blend_np<<<dim3((w + 255) / 256, h, n), 256, 0, s>>>(gray, stats, h, w, bs, v, lut, dist_l, dist_r, blur_l, blur_r);

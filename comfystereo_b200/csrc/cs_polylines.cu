@@ -293,54 +293,36 @@ struct PolyLayout {
     static constexpr int NT = NW * 32, NP = NT * 8, CPT = SHARP ? 4 : 8, SCAP = NT * CPT;
     static constexpr size_t kBytes = 4 * (size_t)(NP + 8) + 4 * (size_t)NP + 4 * (size_t)NP + 2 * 4 * (size_t)(SCAP + 8) +
                                      8 * (size_t)NT + 2 * (size_t)NP + 2 * (size_t)(NP + 16) + 2 * (size_t)NP +
-                                     2 * (size_t)(SCAP + 8) + 2 * 4 * (size_t)SCAP;   // last: staging of the next tile's rows
+                                     2 * (size_t)(SCAP + 8);
     // source columns a CTA can take: every point incl. both sentinels fits the NP slots (4 columns of slack for the
     // 16-byte alignment of the window's first column)
     static constexpr int kCapCols = (NP - 2) / (SHARP ? 2 : 1) - 4;
 };
 
-// One work item = (tile, row, frame, eye); items are numbered row by row, the tiles of both eyes of a row next to each
-// other (they read the same image row).
-struct PolyItem { int eye, frame, y, t0, tw, own, s0, w; int64_t row_off; };
-__device__ __forceinline__ PolyItem poly_item(int idx, const WarpArgs& a, const PolyGeom& g) {
-    PolyItem it;
-    const int nt0 = g.ntiles[0], per_row = nt0 + g.ntiles[1];
-    const int row = idx / per_row, r = idx - row * per_row;
-    it.eye = (r >= nt0) ? 1 : 0;
-    const int tile = it.eye ? r - nt0 : r;
-    it.frame = row / a.h;
-    it.y = row - it.frame * a.h;
-    const int W = a.w;
-    it.t0 = 0; it.tw = W; it.own = W; it.s0 = 0; it.w = W;
-    if (g.tile_w[it.eye] < W) {
-        const int o0 = tile * g.tile_w[it.eye];
-        it.own = min(g.tile_w[it.eye], W - o0);
-        it.t0 = max(o0 - g.ext[it.eye], 0);
-        it.tw = o0 + it.own - it.t0;
-        it.s0 = min(max(it.t0 + g.lo_off[it.eye], 0), W - 1) & ~3;
-        it.w = min(max(it.t0 + it.tw + g.hi_off[it.eye], it.s0 + 1), W) - it.s0;
-    }
-    it.row_off = ((int64_t)it.frame * a.h + it.y) * W;
-    return it;
-}
-// depth + image window of an item by two bulk asynchronous copies, when the window is 16-byte aligned
-__device__ __forceinline__ bool poly_bulk_ok(const PolyItem& it, const WarpArgs& a) {
-    const float* dep = a.depth[it.eye] + it.row_off + it.s0;
-    const uint32_t* img = a.image_u8 + it.row_off + it.s0;
-    return ((reinterpret_cast<uintptr_t>(dep) | reinterpret_cast<uintptr_t>(img)) & 15) == 0 && (it.w & 3) == 0;
-}
-
-// Persistent CTAs: each takes work items from a global counter until none are left.  While an item is processed the
-// depth and image windows of the CTA's NEXT item are already on their way into a staging buffer (TMA bulk copies that
-// complete on an mbarrier), so an item never waits for global memory.
 template <int NW, bool SHARP, int TPS>   // TPS: resident threads per SM the register budget is set for
 __global__ void __launch_bounds__(NW * 32, TPS / (NW * 32))
 k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int* __restrict__ row_list,
-            int* __restrict__ counters, int mode_flags, int total_items) {
+            int* __restrict__ counters, int mode_flags) {
     using L = PolyLayout<NW, SHARP>;
     constexpr int NT = L::NT, NP = L::NP, CPT = L::CPT, SCAP = L::SCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int W = a.w;
+    const int W = a.w, tile = blockIdx.x, y = blockIdx.y, frame = blockIdx.z >> 1, eye = blockIdx.z & 1;
+    if (a.eye[eye].passthrough || tile >= g.ntiles[eye]) return;
+#ifdef CS_POLY_TIMING
+    long long tick_ = cs_clock();
+#endif
+
+    // ---- geometry: own output columns [o0, o0 + own), buckets [t0, t0 + tw), source window [s0, s0 + w)
+    int t0 = 0, tw = W, own = W, s0 = 0, w = W;
+    if (g.tile_w[eye] < W) {
+        const int o0 = tile * g.tile_w[eye];
+        own = min(g.tile_w[eye], W - o0);
+        t0 = max(o0 - g.ext[eye], 0);
+        tw = o0 + own - t0;
+        s0 = min(max(t0 + g.lo_off[eye], 0), W - 1) & ~3;
+        w = min(max(t0 + tw + g.hi_off[eye], s0 + 1), W) - s0;
+    }
+    const int npts = (SHARP ? 2 * w : w) + 2, nsg = npts - 1;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 
     float* XA = reinterpret_cast<float*>(smem_raw);             // [NP + 8]  x in source order; X[1] is 16-byte aligned
@@ -356,79 +338,31 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     uint16_t* SID = reinterpret_cast<uint16_t*>(TMN + NT);       // [NP]
     uint16_t* WSP = SID + NP;                                    // [NP + 16] (holds the source-order ranks during the sort)
     uint16_t* RNK = WSP + 7;                                     //           RNK[1] is 16-byte aligned
-    uint16_t* LIST = WSP + NP + 16;                              // [NP] work lists: deep inversions, hard intervals, columns
+    uint16_t* LIST = WSP + NP + 16;                              // [NP] work lists: deep inversions, then hard intervals
     uint16_t* START = LIST + NP;                                 // [SCAP + 8]
-    float* DSTG = reinterpret_cast<float*>(START + SCAP + 8);    // [SCAP] staging: depth window of the next item
-    uint32_t* ISTG = reinterpret_cast<uint32_t*>(DSTG + SCAP);   // [SCAP] staging: image window of the next item
     __shared__ float s_wa[32], s_wb[32];
     __shared__ int s_wr[32];
-    __shared__ int s_nslow, s_nhard, s_next, s_nflag, s_item[2];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_nslow, s_nhard, s_next, s_nflag;
     __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
-
-    // first item of this CTA and its copies
-    if (t == 0) {
-        mbar_init(&s_bar, 1);
-        const int first = atomicAdd(&counters[2], 1);
-        s_item[0] = first;
-        if (first < total_items) {
-            const PolyItem nx = poly_item(first, a, g);
-            if (poly_bulk_ok(nx, a)) {
-                mbar_expect_tx(&s_bar, 2u * (uint32_t)nx.w * 4u);
-                bulk_g2s(DSTG, a.depth[nx.eye] + nx.row_off + nx.s0, (uint32_t)nx.w * 4u, &s_bar);
-                bulk_g2s(ISTG, a.image_u8 + nx.row_off + nx.s0, (uint32_t)nx.w * 4u, &s_bar);
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t parity = 0;
-    bool give_up = false;
-
-    for (int iter = 0;; ++iter) {
-    const int item = s_item[iter & 1];
-    if (item >= total_items) break;
-    const PolyItem me = poly_item(item, a, g);
-    const int eye = me.eye, frame = me.frame, y = me.y, t0 = me.t0, tw = me.tw, own = me.own, s0 = me.s0, w = me.w;
-    const int npts = (SHARP ? 2 * w : w) + 2, nsg = npts - 1;
-    const bool bulk = poly_bulk_ok(me, a);
-#ifdef CS_POLY_TIMING
-    long long tick_ = cs_clock();
-#endif
     if (t == 0) {
         s_nslow = 0; s_nhard = 0; s_next = 0; s_nflag = 0;
         s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;
         s_tab.START = START; s_tab.w = w; s_tab.npts = npts; s_tab.nsg = nsg; s_tab.t0 = t0;
-        s_item[(iter + 1) & 1] = atomicAdd(&counters[2], 1);     // the item after this one (read after the next barrier)
     }
 
     // ---- A: depth + image of this thread's CPT source columns -> 8 points in registers
-    const int64_t row_off = me.row_off;
+    const int64_t row_off = ((int64_t)frame * a.h + y) * W;
     const int c0 = t * CPT, i0 = 1 + 8 * t;
     float v[8];
     {
-        const float* dep = a.depth[eye] + row_off + s0;
-        const uint32_t* img = a.image_u8 + row_off + s0;
-        const bool vec = ((reinterpret_cast<uintptr_t>(dep) | reinterpret_cast<uintptr_t>(img)) & 15) == 0;
         float scale;
         const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
+        const float* dep = a.depth[eye] + row_off + s0;
+        const uint32_t* img = a.image_u8 + row_off + s0;
         float dv[CPT];
         uint32_t iv[CPT];
-        if (bulk) {
-            mbar_wait(&s_bar, parity);        // this item's windows have landed in the staging buffers
-            parity ^= 1u;
-#pragma unroll
-            for (int q = 0; q < CPT / 4; ++q) {
-                const bool in4 = c0 + 4 * q < w;
-                const float4 d4 = in4 ? reinterpret_cast<const float4*>(DSTG + c0)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint4 i4 = in4 ? reinterpret_cast<const uint4*>(ISTG + c0)[q] : make_uint4(0u, 0u, 0u, 0u);
-                dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
-                iv[4 * q] = i4.x; iv[4 * q + 1] = i4.y; iv[4 * q + 2] = i4.z; iv[4 * q + 3] = i4.w;
-            }
-            // the column after the last repeats it (colour of the right sentinel)
-#pragma unroll
-            for (int j = 0; j < CPT; ++j)
-                if (c0 + j == w) iv[j] = ISTG[w - 1];
-        } else if (vec && c0 + CPT <= w) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(dep) | reinterpret_cast<uintptr_t>(img)) & 15) == 0;
+        if (vec && c0 + CPT <= w) {
 #pragma unroll
             for (int q = 0; q < CPT / 4; ++q) {
                 const float4 d4 = __ldg(reinterpret_cast<const float4*>(dep + c0) + q);
@@ -478,14 +412,13 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         reinterpret_cast<float4*>(X + i0)[0] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(X + i0)[1] = make_float4(v[4], v[5], v[6], v[7]);
 #pragma unroll
-        for (int q = 0; q < CPT / 4; ++q)
+        for (int q = 0; q < CPT / 4; ++q) {
             reinterpret_cast<float4*>(Q + 1 + c0)[q] = make_float4(qv[4 * q], qv[4 * q + 1], qv[4 * q + 2], qv[4 * q + 3]);
-        if (t == 0) { X[0] = (float)(-1.0 * W); Q[0] = 0.0f; IMGP[0] = iv[0]; }
-#pragma unroll
-        for (int q = 0; q < CPT / 4; ++q)
             reinterpret_cast<uint4*>(IMGP + 1 + c0)[q] = make_uint4(iv[4 * q], iv[4 * q + 1], iv[4 * q + 2], iv[4 * q + 3]);
-        // vector path: the pad after the last column (the other paths loaded it in place)
-        if (!bulk && c0 + CPT == w && vec) IMGP[1 + w] = iv[CPT - 1];
+        }
+        if (t == 0) { X[0] = (float)(-1.0 * W); Q[0] = 0.0f; IMGP[0] = iv[0]; }
+        // vector path: the pad after the last column (the scalar path loaded it in place)
+        if (c0 + CPT == w && vec) IMGP[1 + w] = iv[CPT - 1];
     }
 
     CS_TICK(0);
@@ -739,7 +672,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     CS_TICK(8);
     __syncthreads();
     CS_TICK(9);
-    give_up = false;
+    bool give_up = false;
     {
         const int nflag = s_nflag;
         for (int q = wid; q < nflag; q += NW) {     // one column per warp at a time
@@ -758,8 +691,6 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         const int rowid = (frame * 2 + eye) * a.h + y;
         if (atomicOr(&row_flags[rowid], 1) == 0) row_list[atomicAdd(&counters[1], 1)] = rowid;
     }
-    __syncthreads();   // the tables are free for the next item; s_item[(iter + 1) & 1] is visible
-    }   // items
 }
 
 static size_t exact_smem(int w, int sharp, int act_cap) {
@@ -866,24 +797,14 @@ static bool plan_for(int nw, const WarpArgs& a, bool sharp, bool force_tiles, Po
 template <int NW, bool SHARP, int TPS>
 static cudaError_t launch_tiles_occ(const WarpArgs& a, const PolyPlan& p, int* counters, int* flags, int* list, cudaStream_t s) {
     using L = PolyLayout<NW, SHARP>;
-    static int ctas_per_sm = 0, sms = 0;   // benign race: both are idempotent
-    if (!ctas_per_sm) {
+    static bool attr_done = false;   // benign race: the attribute is idempotent
+    if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_polylines<NW, SHARP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes);
         if (e != cudaSuccess) return e;
-        int dev = 0, occ = 0, nsm = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_polylines<NW, SHARP, TPS>, NW * 32, L::kBytes)) != cudaSuccess) return e;
-        if (occ < 1) return cudaErrorInvalidConfiguration;
-        sms = nsm; ctas_per_sm = occ;
+        attr_done = true;
     }
-    // persistent CTAs: as many as fit on the device at once; they share a work counter
-    const long long total = (long long)a.n * a.h * (p.g.ntiles[0] + p.g.ntiles[1]);
-    if (total > 0x7FFFFFF0ll) return cudaErrorInvalidValue;
-    const long long slots = (long long)sms * ctas_per_sm;
-    const int grid = (int)(total < slots ? total : slots);
     prof_begin(K_POLY_FAST, s);
-    k_polylines<NW, SHARP, TPS><<<grid, NW * 32, L::kBytes, s>>>(a, p.g, flags, list, counters, a.flags, (int)total);
+    k_polylines<NW, SHARP, TPS><<<dim3(p.max_tiles, a.h, 2 * a.n), NW * 32, L::kBytes, s>>>(a, p.g, flags, list, counters, a.flags);
     prof_end(K_POLY_FAST, s);
     count_launch();
     return cudaGetLastError();

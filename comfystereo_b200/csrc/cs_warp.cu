@@ -112,8 +112,18 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
     uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
     const size_t simg_bytes = ((size_t)w * 4 + 15) & ~(size_t)15;
     unsigned char* smem_rest = smem_raw + simg_bytes;
-    {
-        const uint32_t* gimg = a.image_u8 + (int64_t)frame * a.h * w + row_off;
+    // one bulk asynchronous copy (TMA) when the row is 16-byte aligned: it lands while the winners are being resolved
+    // and is waited for right before the first gather; otherwise a coalesced loop
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t* gimg = a.image_u8 + (int64_t)frame * a.h * w + row_off;
+    const bool bulk = ((reinterpret_cast<uintptr_t>(gimg) & 15) == 0) && ((w & 3) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)w * 4u);
+            bulk_g2s(simg, gimg, (uint32_t)w * 4u, &s_bar);
+        }
+    } else {
         for (int x = threadIdx.x; x < w; x += blockDim.x) simg[x] = gimg[x];
     }
     const uint32_t* img = simg;
@@ -145,6 +155,7 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
           }
         }
         __syncthreads();
+        if (bulk) mbar_wait(&s_bar, 0);   // the image row has landed
         if (FILL == CS_FILL_INVERSE_POST) {
             uint32_t* bits = reinterpret_cast<uint32_t*>(key + w);
             const int wpad = nwords << 5;
@@ -212,6 +223,7 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
             if ((threadIdx.x & 31) == 0) bits[x >> 5] = b;
         }
         __syncthreads();
+        if (bulk) mbar_wait(&s_bar, 0);   // the image row has landed
         if (FILL == CS_FILL_NONE) {
             for (int x = threadIdx.x; x < w; x += blockDim.x) {
                 int s = win[x];
