@@ -340,6 +340,10 @@ def main():
     k_bytes_px = {"k_prepare": 24 + 8, "k_edge_dist": 4 + 2, "k_blur_blend": 4 + 2 + 8 + 24, "k_depth_out": 4 + 24,
                   "k_warp_rows": 24, "k_polylines": 24, "k_polylines_exact": 24, "k_hybrid_splat": 24,
                   "k_hybrid_gapfill": 16, "k_gpuwarp": 12 + 8 + 24 + 4, "k_compose": 8 + 24 + 8}
+    if args.mode in ("left-right", "right-left", "top-bottom", "bottom-top") and abs(args.balance) < 0.999:
+        # these kernels write the composed float32 tensor + mask themselves (24 + 8 B/px) instead of 8 B/px of RGBX8 eyes
+        for k in ("k_polylines", "k_warp_rows"):
+            k_bytes_px[k] = 8 + 8 + 32
     timed = {k: v for k, v in kernels.items() if k != "misc"}
     total_k_ms = sum(v[0] for v in timed.values()) or 1.0
     dom = max(timed, key=lambda k: timed[k][0]) if timed else None

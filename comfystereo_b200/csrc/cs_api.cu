@@ -210,11 +210,21 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
         a.conv = (float)p->convergence_point;
         a.scratch = ws.warp_scratch; a.scratch_bytes = ws.warp_scratch_bytes;
         a.flags = flags;
+        // Polylines and the row techniques write the composed tensors themselves in the side-by-side / top-bottom modes
+        // (when both eyes are warped)
+        const bool rows = p->fill == CS_FILL_NONE || p->fill == CS_FILL_NAIVE || p->fill == CS_FILL_NAIVE_INTERP ||
+                          p->fill == CS_FILL_INVERSE || p->fill == CS_FILL_NONE_POST || p->fill == CS_FILL_INVERSE_POST;
+        const bool fused = (rows || p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP) &&
+                           p->mode >= CS_MODE_LEFT_RIGHT && p->mode <= CS_MODE_BOTTOM_TOP &&
+                           !eye[0].passthrough && !eye[1].passthrough && !(flags & 16);
+        if (fused) { a.fused_stereo = stereo; a.fused_mask = mask; a.fused_mode = p->mode; }
         if (!(eye[0].passthrough && eye[1].passthrough)) CS_CUDA(launch_fill(a, s), "warp/fill");
-        // an eye whose divergence is < 0.001 is the quantised input itself (SIG:1536, 1539)
-        const uint32_t* L = eye[0].passthrough ? ws.image_u8 : ws.eye_out[0];
-        const uint32_t* R = eye[1].passthrough ? ws.image_u8 : ws.eye_out[1];
-        CS_CUDA(launch_compose(L, R, n, h, w, p->mode, stereo, mask, s), "compose");
+        if (!fused) {
+            // an eye whose divergence is < 0.001 is the quantised input itself (SIG:1536, 1539)
+            const uint32_t* L = eye[0].passthrough ? ws.image_u8 : ws.eye_out[0];
+            const uint32_t* R = eye[1].passthrough ? ws.image_u8 : ws.eye_out[1];
+            CS_CUDA(launch_compose(L, R, n, h, w, p->mode, stereo, mask, s), "compose");
+        }
     } else {
         GpuWarpArgs g;
         memset(&g, 0, sizeof(g));

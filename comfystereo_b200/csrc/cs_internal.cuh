@@ -148,6 +148,7 @@ __device__ __forceinline__ uint32_t pack_rgbx(int r, int g, int b, int x = 0) {
 }
 
 // ---------------------------------------------------------------- launchers (host)
+
 struct EyeSpec {          // one eye of one call
     double div_px, sep_px; // signed, in pixels (SIG:1602-1603)
     int passthrough;       // divergence*(1 +- balance) < 0.001 -> the eye is the input image
@@ -168,7 +169,21 @@ struct WarpArgs {
     void* scratch;              // technique-specific device scratch
     size_t scratch_bytes;
     int flags;                  // bit 0: polylines -- skip the fast sweep, replay every row exactly (tests)
+    // Polylines only, side-by-side / top-bottom modes: the sweep writes the composed float32 tensors itself (C1 + M1 + O1,
+    // SIG:1543-1552, GS:355-378) instead of the RGBX8 eye image that k_compose would read back.  nullptr: classic output.
+    float* fused_stereo;        // [n][ho][wo][3]
+    float* fused_mask;          // [n][ho][wo]
+    int fused_mode;             // CS_MODE_LEFT_RIGHT .. CS_MODE_BOTTOM_TOP
 };
+
+// composed position of eye pixel (frame, y, x): index of the pixel in the [n][ho][wo] output
+__device__ __forceinline__ int64_t fused_index(const WarpArgs& a, int eye, int frame, int y, int x) {
+    const bool sbs = a.fused_mode == CS_MODE_LEFT_RIGHT || a.fused_mode == CS_MODE_RIGHT_LEFT;
+    const bool second = (a.fused_mode == CS_MODE_LEFT_RIGHT || a.fused_mode == CS_MODE_TOP_BOTTOM) ? (eye == 1) : (eye == 0);
+    const int wo = sbs ? 2 * a.w : a.w, ho = sbs ? a.h : 2 * a.h;
+    const int ox = x + ((sbs && second) ? a.w : 0), oy = y + ((!sbs && second) ? a.h : 0);
+    return ((int64_t)frame * ho + oy) * wo + ox;
+}
 
 void count_launch();
 // Optional per-kernel timing (bench.py): CUDA events recorded on the launch stream around every kernel.
@@ -227,3 +242,4 @@ cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const flo
                                    int depth_u8, void* cdl, void* cdr, uint8_t* cmask, cudaStream_t s);
 
 }  // namespace cs
+

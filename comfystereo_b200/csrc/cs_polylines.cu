@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kExactThreads) k_polylines_exact(const WarpArg
         if (threadIdx.x == 0) {
             const int64_t row_off = (int64_t)frame * a.h * w + (int64_t)y * w;
             const uint32_t* img = a.image_u8 + row_off;
-            uint32_t* out = a.out[eye] + row_off;
+            uint32_t* out = a.fused_stereo ? nullptr : a.out[eye] + row_off;
             int nact = 0, sgp = 0, pi = 0;
             bool overflow = false;
             for (int col = 0; col < w; ++col) {
@@ -262,7 +262,16 @@ __global__ void __launch_bounds__(kExactThreads) k_polylines_exact(const WarpArg
                     }
                     ++pi;
                 }
-                out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
+                if (a.fused_stereo) {
+                    const int64_t o = fused_index(a, eye, frame, y, col);
+                    const int r = (int)color[0], gch = (int)color[1], b = (int)color[2];
+                    a.fused_stereo[o * 3 + 0] = (float)r / 255.0f;
+                    a.fused_stereo[o * 3 + 1] = (float)gch / 255.0f;
+                    a.fused_stereo[o * 3 + 2] = (float)b / 255.0f;
+                    a.fused_mask[o] = (r + gch + b == 0) ? 1.0f : 0.0f;
+                } else {
+                    out[col] = pack_rgbx((int)color[0], (int)color[1], (int)color[2]);
+                }
             }
             if (overflow) atomicOr(status, 1);
         }
@@ -343,7 +352,9 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     __shared__ float s_wa[32], s_wb[32];
     __shared__ int s_wr[32];
     __shared__ int s_nslow, s_nhard, s_next, s_nflag;
+    __shared__ float s_q255[256];     // k / 255.0f (GS:365-378), for the fused composed output
     __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
+    for (int k = t; k < 256; k += NT) s_q255[k] = (float)k / 255.0f;
     if (t == 0) {
         s_nslow = 0; s_nhard = 0; s_next = 0; s_nflag = 0;
         s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;
@@ -654,7 +665,19 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     // ---- E: sweep.  Warps take 32-column blocks from a shared counter (blocks inside folds cost several times more).
     // Columns the float32 path cannot certify are listed and redone afterwards, all at once: inside the sweep each of
     // them would stall its whole warp for longer than a block takes, and the slowest warp sets the CTA's lifetime.
-    uint32_t* out = a.out[eye] + row_off + t0;
+    uint32_t* out = a.fused_stereo ? nullptr : a.out[eye] + row_off + t0;
+    const uint64_t pol = policy_evict_first();
+    // one finished pixel: the RGBX8 eye image, or (fused) its place in the composed float32 tensor and the black-pixel mask
+    auto emit = [&](int col, uint32_t px) {
+        if (out) { out[col] = px; return; }
+        const int64_t o = fused_index(a, eye, frame, y, col + t0);
+        const uint32_t r = px & 255u, gch = (px >> 8) & 255u, b = (px >> 16) & 255u;
+        float* dst = a.fused_stereo + o * 3;
+        st_stream_f1(dst, s_q255[r], pol);
+        st_stream_f1(dst + 1, s_q255[gch], pol);
+        st_stream_f1(dst + 2, s_q255[b], pol);
+        st_stream_f1(a.fused_mask + o, (r + gch + b == 0u) ? 1.0f : 0.0f, pol);
+    };
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
     const bool all_exact = (mode_flags & 8) != 0;
     for (;;) {
@@ -663,11 +686,12 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         blk = __shfl_sync(0xffffffffu, blk, 0);
         if (blk >= nblk) break;
         const int col = first + (blk << 5) + lane;
-        if (col >= tw) continue;
+        const bool in = col < tw;
         uint32_t px = 0;
-        const bool ok = poly::fast_column<SHARP>(tab, col, &px) && !all_exact;
-        if (ok) out[col] = px;
-        else LIST[atomicAdd(&s_nflag, 1)] = (uint16_t)col;
+        const bool ok = in && poly::fast_column<SHARP>(tab, col, &px) && !all_exact;
+        if (in && !ok) LIST[atomicAdd(&s_nflag, 1)] = (uint16_t)col;
+        // (pixel by pixel: the 128-bit warp-collective form used by the row kernels measured 2 % slower here)
+        if (ok) emit(col, px);
     }
     CS_TICK(8);
     __syncthreads();
@@ -679,7 +703,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
             const int col = LIST[q];
             uint32_t px = poly::exact_column_warp<SHARP>(s_tab, col);
             if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
-            if (lane == 0) out[col] = px;
+            if (lane == 0) emit(col, px);
         }
 #ifdef CS_POLY_TIMING
         if (t == 0) { atomicAdd(&g_poly_ticks[12], (unsigned long long)nflag); atomicAdd(&g_poly_ticks[13], 1ull); }
@@ -811,10 +835,8 @@ static cudaError_t launch_tiles_occ(const WarpArgs& a, const PolyPlan& p, int* c
 }
 template <int NW, bool SHARP>
 static cudaError_t launch_tiles(const WarpArgs& a, const PolyPlan& p, int* counters, int* flags, int* list, cudaStream_t s) {
-    static int occ = -1;
-    if (occ < 0) { const char* v = getenv("COMFYSTEREO_POLY_OCC"); occ = v ? atoi(v) : 0; }
-    if (occ == 1) return launch_tiles_occ<NW, SHARP, 768>(a, p, counters, flags, list, s);
-    if (occ == 2) return launch_tiles_occ<NW, SHARP, 512>(a, p, counters, flags, list, s);
+    // 64 registers per thread (1024 resident threads per SM): 80- and 92-register builds have no spills but measured
+    // slower -- the occupancy they cost outweighs the 48 bytes of spilled loop invariants
     return launch_tiles_occ<NW, SHARP, 1024>(a, p, counters, flags, list, s);
 }
 

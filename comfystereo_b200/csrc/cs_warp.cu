@@ -106,7 +106,26 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
     float scale;
     const Normalizer norm = eye_normalizer(a, eye, frame, &scale);
     const int64_t row_off = (int64_t)y * w;
-    uint32_t* out = a.out[eye] + (int64_t)frame * a.h * w + row_off;
+    uint32_t* out = a.fused_stereo ? nullptr : a.out[eye] + (int64_t)frame * a.h * w + row_off;
+    // one finished pixel: the RGBX8 eye image, or (fused: side-by-side / top-bottom modes) its place in the composed
+    // float32 tensor and the black-pixel mask (C1 + M1 + O1, SIG:1543-1552, GS:355-378) -- no k_compose pass then
+    __shared__ float s_q255[256];
+    if (a.fused_stereo) for (int k = threadIdx.x; k < 256; k += blockDim.x) s_q255[k] = (float)k / 255.0f;   // visible after the first barrier
+    const uint64_t pol = policy_evict_first();
+    // (pixel by pixel: three 4-byte stores at a 12-byte stride per warp merge in L2; a warp-collective version that
+    // shuffles the pixels into 128-bit stores measured 10 % slower)
+    auto emit_w = [&](int x, uint32_t px, bool in) {
+        if (!in) return;
+        if (out) { out[x] = px; return; }
+        const int64_t o = fused_index(a, eye, frame, y, x);
+        const uint32_t r = px & 255u, g = (px >> 8) & 255u, b = (px >> 16) & 255u;
+        float* dst = a.fused_stereo + o * 3;
+        st_stream_f1(dst, s_q255[r], pol);
+        st_stream_f1(dst + 1, s_q255[g], pol);
+        st_stream_f1(dst + 2, s_q255[b], pol);
+        st_stream_f1(a.fused_mask + o, (r + g + b == 0u) ? 1.0f : 0.0f, pol);
+    };
+
     // the RGBX8 row is gathered at shifted columns: stage it in shared memory with one coalesced pass (the scattered
     // global reads were 31 % of this kernel's stall samples), and fetch depth four columns ahead of the FP64 chain
     uint32_t* simg = reinterpret_cast<uint32_t*>(smem_raw);
@@ -165,7 +184,10 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
                 if ((threadIdx.x & 31) == 0) bits[x >> 5] = b;
             }
             __syncthreads();
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+                uint32_t px_ = 0;
+                const bool in_ = x < w;
+                if (in_) {
                 unsigned long long k = key[x];
                 uint32_t px;
                 if (k) px = (img[0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull)] & 0x00FFFFFFu) | 0x01000000u;
@@ -179,15 +201,22 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
                         px = interp_px(x, xl, xr, w, pl, pr);
                     }
                 }
-                out[x] = px;
+                px_ = px;
+                }
+                emit_w(x, px_, in_);
             }
             return;
         }
-        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+            uint32_t px_ = 0;
+            const bool in_ = x < w;
+            if (in_) {
             unsigned long long k = key[x];
             uint32_t px = 0;
             if (k) px = (img[0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull)] & 0x00FFFFFFu) | 0x01000000u;
-            out[x] = px;
+            px_ = px;
+            }
+            emit_w(x, px_, in_);
         }
         return;
     } else {
@@ -225,12 +254,20 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
         __syncthreads();
         if (bulk) mbar_wait(&s_bar, 0);   // the image row has landed
         if (FILL == CS_FILL_NONE) {
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+                uint32_t px_ = 0;
+                const bool in_ = x < w;
+                if (in_) {
                 int s = win[x];
-                out[x] = (s != empty) ? ((img[s] & 0x00FFFFFFu) | 0x01000000u) : 0u;
+                px_ = (s != empty) ? ((img[s] & 0x00FFFFFFu) | 0x01000000u) : 0u;
+                }
+                emit_w(x, px_, in_);
             }
         } else if (FILL == CS_FILL_NONE_POST) {
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+                uint32_t px_ = 0;
+                const bool in_ = x < w;
+                if (in_) {
                 int s = win[x];
                 uint32_t px;
                 if (s != empty) px = (img[s] & 0x00FFFFFFu) | 0x01000000u;
@@ -240,12 +277,17 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
                     if (xl < 0 && xr >= w) px = 0u;
                     else px = interp_px(x, xl, xr, w, xl >= 0 ? img[win[xl]] : 0u, xr < w ? img[win[xr]] : 0u);
                 }
-                out[x] = px;
+                px_ = px;
+                }
+                emit_w(x, px_, in_);
             }
         } else if (FILL == CS_FILL_NAIVE) {
             double adiv = fabs(div_px);
             const int reach = (int)adiv + 1;  // range(1, abs(int(div_px)) + 2), SIG:1896
-            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+                uint32_t px_ = 0;
+                const bool in_ = x < w;
+                if (in_) {
                 int s = win[x];
                 uint32_t px = 0;
                 if (s != empty) px = (img[s] & 0x00FFFFFFu) | 0x01000000u;
@@ -254,7 +296,9 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
                     if (dr <= reach && dr <= dl) px = img[win[x + dr]] & 0x00FFFFFFu;
                     else if (dl <= reach) px = img[win[x - dl]] & 0x00FFFFFFu;
                 }
-                out[x] = px;
+                px_ = px;
+                }
+                emit_w(x, px_, in_);
             }
         } else {  // naive_interpolating, SIG:1871-1892
             // An "anchor" is a pixel that stops the reference's right-border scan: non-black and filled.  A fill started
@@ -317,8 +361,14 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
                 }
             }
             __syncthreads();
-            for (int x = threadIdx.x; x < w; x += blockDim.x)
-                out[x] = row[x] | (((bits[x >> 5] >> (x & 31)) & 1u) << 24);
+            for (int x = threadIdx.x; x - (int)(threadIdx.x & 31) < w; x += blockDim.x) {
+                uint32_t px_ = 0;
+                const bool in_ = x < w;
+                if (in_) {
+                px_ = row[x] | (((bits[x >> 5] >> (x & 31)) & 1u) << 24);
+                }
+                emit_w(x, px_, in_);
+            }
         }
     }
 }

@@ -171,6 +171,55 @@ def test_ragged_sizes_against_oracle(node, oracle, shape, fill):
                 assert np.array_equal(got[3], want[3])
 
 
+@pytest.mark.parametrize("mode", ["left-right", "right-left", "top-bottom", "bottom-top"])
+def test_polylines_composes_in_the_sweep(node, oracle, mode):
+    """In the side-by-side / top-bottom modes the Polylines sweep writes the composed float32 tensor and the mask itself.
+    Same bytes as the separate k_compose pass (test flag 16), with the sequential kernel (flag 1), tiles (flag 4), and the
+    oracle; a black source region makes the mask non-trivial."""
+    from comfystereo_b200 import _lib
+    img = syn.make_image(2, 96, 352, seed=13, black_box=True)
+    dep = syn.make_depth(2, 96, 352, "scene", seed=13)
+    lib = _lib.lib()
+    for fill in ("Fill - Polylines Sharp", "Fill - Polylines Soft"):
+        got, p = run(node, img, dep, fill_technique=fill, modes=mode, divergence=6.0, separation=0.4)
+        want = oracle.node_generate(img, dep, **p)
+        for g, w_ in zip(got, want):
+            assert np.array_equal(q8(g), q8(w_))
+        assert np.array_equal(got[3], want[3]) and got[3].sum() > 0
+        for flags in (16, 1, 4, 8):
+            lib.cs_set_test_flags(flags)
+            try:
+                alt, _ = run(node, img, dep, fill_technique=fill, modes=mode, divergence=6.0, separation=0.4)
+            finally:
+                lib.cs_set_test_flags(0)
+            for a_, b_ in zip(got, alt):
+                assert np.array_equal(a_, b_), flags
+
+
+@pytest.mark.parametrize("fill", ["No fill", "Fill - Naive", "Fill - Naive interpolating", "No fill - Reverse projection"])
+def test_row_techniques_compose_in_the_fill_kernel(node, oracle, fill):
+    """The row kernels write the composed tensor and the mask themselves in the side-by-side / top-bottom modes: same
+    bytes as the separate k_compose pass (test flag 16) and as the oracle, odd width (no vector path) included."""
+    from comfystereo_b200 import _lib
+    lib = _lib.lib()
+    for w in (352, 333):
+        img = syn.make_image(2, 80, w, seed=17, black_box=True)
+        dep = syn.make_depth(2, 80, w, "scene", seed=17)
+        for mode in ("left-right", "right-left", "top-bottom", "bottom-top"):
+            got, p = run(node, img, dep, fill_technique=fill, modes=mode, divergence=7.0, separation=-0.3)
+            want = oracle.node_generate(img, dep, **p)
+            for g, w_ in zip(got, want):
+                assert np.array_equal(q8(g), q8(w_))
+            assert np.array_equal(got[3], want[3]) and got[3].sum() > 0
+            lib.cs_set_test_flags(16)
+            try:
+                alt, _ = run(node, img, dep, fill_technique=fill, modes=mode, divergence=7.0, separation=-0.3)
+            finally:
+                lib.cs_set_test_flags(0)
+            for a_, b_ in zip(got, alt):
+                assert np.array_equal(a_, b_)
+
+
 def test_progress_is_reported_per_chunk_and_depth_batch_may_be_longer(node, oracle, monkeypatch):
     """GS:173 / GS:262: the reference moves its progress bar per sub-batch / per frame; the node reports every chunk of
     frames as its results land (in order, on the calling thread) and the updates add up to the batch size.  A depth
