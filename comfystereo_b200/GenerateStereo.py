@@ -6,16 +6,17 @@ blurred_depthmap_left/right [N,H,W,3], no_fill_imperfect_mask [N,Hm,Wm]).  Insid
 handed to the sm_100a library in one call: frames stream host -> GPU -> host in overlapped chunks
 (and are sharded frame-wise over the visible GPUs when COMFYSTEREO_MULTI_GPU is set).
 
-"GPU Warp (Fast)" reproduces the reference's forward_warp_gpu (SIG:277-450), which is what the reference runs when
-moderngl is not importable; with moderngl installed the reference switches to its OpenGL mesh rasteriser
-(forward_warp_mesh, SIG:1067-1071), whose output depends on the GL driver and is not reproduced here.
+"GPU Warp (Fast)" is the reference's forward_warp_gpu (SIG:277-450) by default -- what the reference runs when moderngl
+is not importable -- and bit-exact against it.  With moderngl installed the reference switches to an OpenGL mesh
+rasteriser (forward_warp_mesh, SIG:1067-1071) whose fragments depend on the GL implementation; COMFYSTEREO_GPU_WARP=mesh
+(stereoimage_generation.MODERNGL_AVAILABLE) selects this package's software rasteriser for that mesh instead.
 """
 import os
 
 import torch
 import torch.distributed
 
-from . import engine
+from . import engine, stereoimage_generation
 
 try:  # inside ComfyUI
     from comfy.utils import ProgressBar
@@ -56,7 +57,7 @@ class StereoImageNode:
                 "fill_technique": (list(FILL_TECHNIQUES), {
                     "default": "GPU Warp (Fast)",
                     "tooltip": "How disoccluded areas are treated. All techniques run as B200 CUDA kernels. "
-                               "GPU Warp (Fast) = the reference's scatter warp (forward_warp_gpu), not its moderngl mesh rasteriser."}),
+                               "GPU Warp (Fast) = the reference's scatter warp (forward_warp_gpu); COMFYSTEREO_GPU_WARP=mesh switches to the mesh warp (forward_warp_mesh)."}),
             },
             "optional": {
                 "divergence": ("FLOAT", {"default": 4.5, "min": 0.05, "max": 15, "step": 0.01,
@@ -94,6 +95,8 @@ class StereoImageNode:
                  depth_blur_vert_smooth=0, batch_size=4):
         key = engine.FILL_NAME_TO_KEY.get(fill_technique, 'gpu_warp')   # unknown names -> GPU Warp, GS:102
         gpu_branch = key == 'gpu_warp'
+        if gpu_branch and stereoimage_generation.MODERNGL_AVAILABLE:     # SIG:1068-1071
+            key = 'gpu_warp_mesh'
         total = len(image)
         pbar = ProgressBar(total)
         image = image.float() if image.dtype != torch.float32 else image

@@ -15,7 +15,7 @@ ERRORS = {-1: "CS_ERR_ARG", -2: "CS_ERR_CUDA", -3: "CS_ERR_DEVICE", -4: "CS_ERR_
           -5: "CS_ERR_UNSUPPORTED", -6: "CS_ERR_MODE"}
 
 FILL_KEYS = ["none", "naive", "naive_interpolating", "polylines_soft", "polylines_sharp", "inverse",
-             "hybrid_edge", "gpu_warp", "none_post", "inverse_post", "hybrid_edge_plus"]   # index = cs_fill
+             "hybrid_edge", "gpu_warp", "none_post", "inverse_post", "hybrid_edge_plus", "gpu_warp_mesh"]   # index = cs_fill
 MODES = ["left-right", "right-left", "top-bottom", "bottom-top", "red-cyan-anaglyph", "left-only",
          "only-right", "cyan-red-reverseanaglyph"]           # index = cs_mode
 
@@ -61,6 +61,8 @@ SIGNATURES = {
     "cs_warp_fill": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _SZ, _P]),
     "cs_warp_fill_scratch_bytes": (_SZ, [_I, _I, _I]),
     "cs_forward_warp": (_I, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _SZ, _P]),
+    "cs_forward_warp_mesh": (_I, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _SZ, _P]),
+    "cs_forward_warp_mesh_scratch_bytes": (_SZ, [_I, _I, _I]),
     "cs_quantize_image": (_I, [_P, _I, _I, _I, _P, _P]),
     "cs_compose": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cs_stereo_batch": (_I, [_PP, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),

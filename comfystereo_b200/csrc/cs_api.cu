@@ -58,9 +58,11 @@ static bool is_cpu_technique(int fill) {
     return (fill >= CS_FILL_NONE && fill <= CS_FILL_HYBRID_EDGE) || (fill >= CS_FILL_NONE_POST && fill <= CS_FILL_HYBRID_EDGE_PLUS);
 }
 
+static bool is_gpu_warp(int fill) { return fill == CS_FILL_GPU_WARP || fill == CS_FILL_GPU_WARP_MESH; }
+
 static int check_params(const cs_params* p) {
     if (!p) return fail(CS_ERR_ARG, "params is NULL");
-    if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_HYBRID_EDGE_PLUS) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
+    if (p->fill < CS_FILL_NONE || p->fill > CS_FILL_GPU_WARP_MESH) return fail(CS_ERR_ARG, "unknown fill %d", p->fill);
     if (p->mode < CS_MODE_LEFT_RIGHT || p->mode > CS_MODE_CYAN_RED) return fail(CS_ERR_MODE, "Unknown mode");
     if (p->depth_h < 0 || p->depth_w < 0 || (p->depth_h > 0) != (p->depth_w > 0))
         return fail(CS_ERR_ARG, "depth_h/depth_w must both be 0 or both be positive");
@@ -90,7 +92,7 @@ static void eye_specs(const cs_params* p, int w, EyeSpec eye[2]) {
     const double sep = p->separation;
     eye[0].passthrough = ldiv < 0.001;
     eye[1].passthrough = rdiv < 0.001;
-    if (p->fill == CS_FILL_GPU_WARP) {
+    if (is_gpu_warp(p->fill)) {
         const double ldiv_px = (ldiv / 100.0) * w, rdiv_px = (rdiv / 100.0) * w, sep_px = (sep / 100.0) * w;
         eye[0].div_px = +ldiv_px; eye[0].sep_px = -sep_px;
         eye[1].div_px = -rdiv_px; eye[1].sep_px = sep_px;
@@ -144,6 +146,9 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
             ws.warp_scratch_bytes = hybrid_plus_scratch_bytes(chunk, h, w);
             ws.warp_scratch = take(ws.warp_scratch_bytes);
         }
+    } else if (p->fill == CS_FILL_GPU_WARP_MESH) {
+        ws.warp_scratch_bytes = mesh_keep_bytes(chunk, h, w);   // the culled topology, one per sub-batch and eye
+        ws.warp_scratch = take(ws.warp_scratch_bytes);
     }
     ws.total = off;
     return ws;
@@ -239,7 +244,12 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
         g.expo = (float)p->stereo_offset_exponent;
         g.conv = (float)p->convergence_point;
         g.stereo = stereo; g.mask = mask;
-        CS_CUDA(launch_gpuwarp(g, s), "gpuwarp");
+        if (p->fill == CS_FILL_GPU_WARP_MESH) {
+            g.keep = (uint8_t*)ws.warp_scratch;
+            CS_CUDA(launch_meshwarp(g, s), "meshwarp");
+        } else {
+            CS_CUDA(launch_gpuwarp(g, s), "gpuwarp");
+        }
     }
     return CS_OK;
 }
@@ -271,7 +281,7 @@ int cs_output_dims(const cs_params* p, int h, int w, int* ho, int* wo, int* hm, 
     if (rc) return rc;
     if (h < 1 || w < 1 || !ho || !wo || !hm || !wm) return fail(CS_ERR_ARG, "bad dims");
     out_dims(p->mode, h, w, ho, wo);
-    if (p->fill == CS_FILL_GPU_WARP) { *hm = h; *wm = w; }   // M2: single-eye shape even for SBS
+    if (is_gpu_warp(p->fill)) { *hm = h; *wm = w; }   // M2: single-eye shape even for SBS
     else { *hm = *ho; *wm = *wo; }                           // M1: shape of the composed image
     return CS_OK;
 }
@@ -419,6 +429,39 @@ int cs_forward_warp(const float* image, const float* depth, int n, int h, int w,
     return CS_OK;
 }
 
+size_t cs_forward_warp_mesh_scratch_bytes(int n, int h, int w) {
+    if (n < 1 || h < 1 || w < 1) return 0;
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(mesh_keep_bytes(n, h, w));
+}
+
+int cs_forward_warp_mesh(const float* image, const float* depth, int n, int h, int w, double div_px, double sep_px,
+                    double exponent, double convergence, float* warped, float* mask, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+    if (!image || !depth || !warped || !mask || !scratch || n < 1 || h < 1 || w < 1)
+        return fail(CS_ERR_ARG, "cs_forward_warp_mesh: bad argument");
+    if (scratch_bytes < cs_forward_warp_mesh_scratch_bytes(n, h, w))
+        return fail(CS_ERR_WORKSPACE, "cs_forward_warp_mesh: scratch too small");
+    if (w > 9000) return fail(CS_ERR_UNSUPPORTED, "cs_forward_warp_mesh: width %d exceeds the 9000-pixel row capacity", w);
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameStats* st = (FrameStats*)scratch;
+    CS_CUDA(launch_init_stats(st, n, s), "init_stats");
+    CS_CUDA(launch_minmax(depth, n, (int64_t)h * w, st, s), "minmax");
+    GpuWarpArgs g;
+    memset(&g, 0, sizeof(g));
+    g.image = image;
+    g.depth[0] = depth; g.depth[1] = depth;
+    g.stats = st;
+    g.use_blur_stats = 0; g.prescale = 0; g.group = n;   // SIG:314-316: "/255 if ANY frame of the batch has max > 1"
+    g.n = n; g.h = h; g.w = w; g.mode = CS_MODE_LEFT_ONLY;
+    g.eye[0].div_px = div_px; g.eye[0].sep_px = sep_px; g.eye[0].passthrough = 0;
+    g.eye[1].passthrough = 1;
+    g.expo = (float)exponent; g.conv = (float)convergence;
+    g.stereo = warped; g.mask = mask;
+    g.keep = (uint8_t*)scratch + align_up((size_t)n * sizeof(FrameStats));
+    CS_CUDA(launch_meshwarp(g, s), "meshwarp");
+    return CS_OK;
+}
+
 int cs_quantize_image(const float* image, int n, int h, int w, uint8_t* image_u8, void* stream) {
     if (!image || !image_u8 || n < 1 || h < 1 || w < 1) return fail(CS_ERR_ARG, "cs_quantize_image: bad argument");
     CS_CUDA(launch_quantize(image, (int64_t)n * h * w, (uint32_t*)image_u8, (cudaStream_t)stream), "quantize");
@@ -455,7 +498,7 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
         // Polylines: rows of any width are tiled (only the 16-bit point indices of the sequential fallback bound them);
         // the other techniques keep one row per CTA in shared memory
         const bool plus = p->fill == CS_FILL_HYBRID_EDGE_PLUS;
-        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (p->fill == CS_FILL_GPU_WARP ? 9000 : 16000));
+        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (is_gpu_warp(p->fill) ? 9000 : 16000));
         if (w > wmax)
             return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
                         "(one row per CTA in shared memory)", w, wmax);
@@ -490,7 +533,8 @@ int cs_polylines_status(const cs_params* p, int chunk, int h, int w, const void*
     // in the most recent chunk.  Synchronous.
     if (!p || !workspace) return fail(CS_ERR_ARG, "cs_polylines_status: bad argument");
     Workspace ws = carve(p, chunk, h, w, const_cast<void*>(workspace));
-    if (!ws.warp_scratch) return fail(CS_ERR_ARG, "cs_polylines_status: not a polylines configuration");
+    if (!ws.warp_scratch || (p->fill != CS_FILL_POLYLINES_SOFT && p->fill != CS_FILL_POLYLINES_SHARP))
+        return fail(CS_ERR_ARG, "cs_polylines_status: not a polylines configuration");
     // scratch layout (cs_polylines.cu): [0] status bits, [1] rows listed for the sequential kernel, ...
     int host[2] = {0, 0};
     cudaError_t e = cudaMemcpy(host, ws.warp_scratch, sizeof(host), cudaMemcpyDeviceToHost);

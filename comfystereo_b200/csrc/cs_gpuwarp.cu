@@ -44,6 +44,47 @@ __device__ __forceinline__ float gw_pow(float ab, float expo) {  // torch.pow sp
     return powf(ab, expo);
 }
 
+// depth scale chain of one (frame, eye): x255 if the sub-batch max <= 1 (SIG:1045), blur, /255 if any frame of the
+// sub-batch > 1 (SIG:314-316, 487-489), then the frame's own min/max normalisation (SIG:317-324, 490-497)
+struct DepthNorm { float pre, dmin, rng; bool div255, flat; };
+__device__ __forceinline__ DepthNorm gw_depth_norm(const GpuWarpArgs& a, int frame, int eye) {
+    const FrameStats st = a.stats[frame];
+    DepthNorm nm;
+    nm.pre = 1.0f;
+    int omin, omax;
+    if (a.use_blur_stats) {
+        omin = eye ? st.r_min : st.l_min; omax = eye ? st.r_max : st.l_max;
+        nm.div255 = gw_group_max(a.stats, frame, a.group, a.n, eye ? 2 : 1) > 1.0f;
+    } else {
+        omin = st.gray_min; omax = st.gray_max;
+        float gm = gw_group_max(a.stats, frame, a.group, a.n, 0);
+        nm.pre = (a.prescale && gm <= 1.0f) ? 255.0f : 1.0f;
+        nm.div255 = gm * nm.pre > 1.0f;
+    }
+    float dmin = ord2f(omin), dmax = ord2f(omax);
+    if (nm.pre != 1.0f) { dmin = dmin * nm.pre; dmax = dmax * nm.pre; }
+    if (nm.div255) { dmin = dmin / 255.0f; dmax = dmax / 255.0f; }
+    const float range = dmax - dmin;
+    nm.flat = !(range > 1e-6f);
+    nm.rng = range < 1e-6f ? 1e-6f : range;
+    nm.dmin = dmin;
+    return nm;
+}
+
+// pixel offset of one depth sample (SIG:326-331, 499-504); *nd = the normalised depth
+__device__ __forceinline__ float gw_offset(const DepthNorm& nm, float dv, float conv, float expo, float div_px,
+                                           float sep_px, float* nd) {
+    if (nm.pre != 1.0f) dv = dv * nm.pre;
+    if (nm.div255) dv = dv / 255.0f;
+    const float n = nm.flat ? 0.0f : (dv - nm.dmin) / nm.rng;
+    *nd = n;
+    const float sh = n - conv;
+    const float sg = (sh > 0.0f) ? 1.0f : ((sh < 0.0f) ? -1.0f : 0.0f);
+    const float od = sg * gw_pow(fabsf(sh), expo);
+    const float m = od * div_px;
+    return m + sep_px;
+}
+
 template <int TPB>   // CTA size the kernel is compiled for (register budget): 256, or 512 for rows that leave room for two CTAs per SM
 __global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
     extern __shared__ __align__(16) float smem_f[];
@@ -103,39 +144,13 @@ __global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
             continue;
         }
         const float div_px = (float)a.eye[eye].div_px, sep_px = (float)a.eye[eye].sep_px;
-        // depth scale chain: x255 if the sub-batch max <= 1 (SIG:1045), blur, /255 if any frame > 1 (SIG:314-316)
-        const FrameStats st = a.stats[frame];
-        float pre = 1.0f;
-        int omin, omax;
-        bool div255;
-        if (a.use_blur_stats) {
-            omin = eye ? st.r_min : st.l_min; omax = eye ? st.r_max : st.l_max;
-            div255 = gw_group_max(a.stats, frame, a.group, a.n, eye ? 2 : 1) > 1.0f;
-        } else {
-            omin = st.gray_min; omax = st.gray_max;
-            float gm = gw_group_max(a.stats, frame, a.group, a.n, 0);
-            pre = (a.prescale && gm <= 1.0f) ? 255.0f : 1.0f;
-            div255 = gm * pre > 1.0f;
-        }
-        float dmin = ord2f(omin), dmax = ord2f(omax);
-        if (pre != 1.0f) { dmin = dmin * pre; dmax = dmax * pre; }
-        if (div255) { dmin = dmin / 255.0f; dmax = dmax / 255.0f; }
-        const float range = dmax - dmin;
-        const bool flat = !(range > 1e-6f);
-        const float rng = range < 1e-6f ? 1e-6f : range;
+        const DepthNorm nm = gw_depth_norm(a, frame, eye);
         const float* dep = a.depth[eye] + (int64_t)frame * h * w + (int64_t)y * w;
 
         for (int x = threadIdx.x; x < w; x += blockDim.x) {
-            float dv = dep[x];
-            if (pre != 1.0f) dv = dv * pre;
-            if (div255) dv = dv / 255.0f;
-            float n = flat ? 0.0f : (dv - dmin) / rng;
+            float n;
+            const float p = gw_offset(nm, dep[x], a.conv, a.expo, div_px, sep_px, &n);
             ndv[x] = n;
-            float sh = n - a.conv;
-            float sg = (sh > 0.0f) ? 1.0f : ((sh < 0.0f) ? -1.0f : 0.0f);
-            float od = sg * gw_pow(fabsf(sh), a.expo);
-            float m = od * div_px;
-            float p = m + sep_px;
             po[x] = p;
             dest[x] = (float)x + p;
         }
@@ -288,6 +303,273 @@ __global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
     // M2: mask = unfilled_left | unfilled_right, [n][h][w]
     float* mrow = a.mask + ((int64_t)frame * h + y) * w;
     for (int x = threadIdx.x; x < w; x += blockDim.x) mrow[x] = ((ubits[x >> 5] >> (x & 31)) & 1u) ? 1.0f : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Mesh warp: forward_warp_mesh (SIG:453-689), what 'GPU Warp (Fast)' runs when the host has ModernGL (SIG:1068-1071).
+//
+// The reference hands the per-pixel vertex grid to OpenGL; which fragments a GPU's rasteriser produces for it, and
+// with what interpolation rounding, is implementation-defined, so there is no bit pattern to be identical to
+// ("parity unpinned": DESIGN.md section 9).  This is a software rasteriser for the same mesh with a fixed, documented
+// rule set -- the one oracle/stereo_oracle.c:orc_mesh_raster restates -- and it IS bit-exact against that:
+//   * vertex (r, c) sits at window X = (clip_x + 1) * W/2, Y = H - (clip_y + 1) * H/2 with the reference's clip
+//     coordinates (SIG:545-551); vertex rows are H/(H-1) apart, so output row j (centre j + 0.5) lies in exactly one
+//     strip r of quads, at fy = (j + 0.5 - Y_r) / (Y_{r+1} - Y_r);
+//   * triangle a = (v00, v10, v01) spans, on that scanline, from the edge v00-v01 to the edge v10-v01; triangle
+//     b = (v11, v10, v01) from v10-v01 to v10-v11 (SIG:513-520); a pixel centre i + 0.5 is covered when
+//     lo <= i + 0.5 < hi (top-left rule for shared edges);
+//   * the fragment's depth is the normalised depth interpolated along the two edges and then across; the larger
+//     (nearer) one wins -- the reference's '<' test on clip_z = (1 - nd) * 1.98 - 0.99 -- and equal depths go to the
+//     triangle drawn first (all a, then all b, SIG:520; each in raster order);
+//   * colours interpolate the same way; uncovered pixels take the nearest covered pixel on the eye's fill side
+//     (SIG:655-683) and the mask is the coverage before that fill (SIG:639).
+// Triangles are culled with the reference's rule (SIG:522-537): kept when max pairwise offset difference < 1.5 in ANY
+// frame of the sub-batch -- one topology per sub-batch (k_mesh_keep), which is why a triangle can be badly stretched
+// in the other frames and why the z-test is needed at all.
+
+__device__ __forceinline__ float mesh_edge(float xa, float xb, float fy) { float t = xb - xa; t = fy * t; return xa + t; }
+__device__ __forceinline__ float mesh_lerp(float a, float b, float t) { float d = b - a; d = t * d; return a + d; }
+__device__ __forceinline__ float mesh_window_y(int q, int h) {
+    const float cy = -(((float)q / (float)(h - 1)) * 2.0f - 1.0f);
+    return (float)h - (cy + 1.0f) * ((float)h / 2.0f);
+}
+__device__ __forceinline__ float mesh_window_x(float dest, int w) {
+    const float cx = (dest / (float)(w - 1)) * 2.0f - 1.0f;
+    return (cx + 1.0f) * ((float)w / 2.0f);
+}
+
+// keep[eye][sub-batch][strip r][quad x]: bit 0 = triangle a kept, bit 1 = triangle b kept.  One CTA per
+// (strip, sub-batch, eye) walks the sub-batch's frames with the two vertex rows' offsets in shared memory.
+__global__ void __launch_bounds__(256) k_mesh_keep(const GpuWarpArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int w = a.w, h = a.h, r = blockIdx.x, g = blockIdx.y, eye = blockIdx.z;
+    if (a.eye[eye].passthrough) return;
+    float* p0 = smem_f;
+    float* p1 = p0 + w;
+    unsigned char* kb = reinterpret_cast<unsigned char*>(p1 + w);
+    for (int x = threadIdx.x; x < w; x += blockDim.x) kb[x] = 0;
+    const float div_px = (float)a.eye[eye].div_px, sep_px = (float)a.eye[eye].sep_px;
+    const int f0 = g * a.group, f1 = min(f0 + a.group, a.n);
+    for (int f = f0; f < f1; ++f) {
+        const DepthNorm nm = gw_depth_norm(a, f, eye);
+        const float* d0 = a.depth[eye] + ((int64_t)f * h + r) * w;
+        __syncthreads();
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            float n;
+            p0[x] = gw_offset(nm, d0[x], a.conv, a.expo, div_px, sep_px, &n);
+            p1[x] = gw_offset(nm, d0[w + x], a.conv, a.expo, div_px, sep_px, &n);
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) {
+            const float o00 = p0[x], o10 = p0[x + 1], o01 = p1[x], o11 = p1[x + 1];
+            const float thr = 1.5f, dd = fabsf(o10 - o01);   // the diagonal both triangles share
+            const bool ka = fabsf(o00 - o10) < thr && fabsf(o00 - o01) < thr && dd < thr;
+            const bool kbb = fabsf(o11 - o10) < thr && fabsf(o11 - o01) < thr && dd < thr;
+            kb[x] |= (unsigned char)((ka ? 1 : 0) | (kbb ? 2 : 0));
+        }
+    }
+    const int ng = (a.n + a.group - 1) / a.group;
+    unsigned char* out = a.keep + (((int64_t)eye * ng + g) * (h - 1) + r) * (int64_t)(w - 1);
+    for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) out[x] = kb[x];
+}
+
+// One CTA per (output row, frame), both eyes in turn, composed into the final stereo layout like k_gpuwarp.
+__global__ void __launch_bounds__(256) k_meshwarp(const GpuWarpArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
+    const int nwords = (w + 31) >> 5;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_f);   // z-buffer: ordered depth << 32 | ~draw order
+    float* X0 = reinterpret_cast<float*>(key + w);
+    float* X1 = X0 + w;
+    float* N0 = X1 + w;
+    float* N1 = N0 + w;
+    uint32_t* fbits = reinterpret_cast<uint32_t*>(N1 + w);    // covered
+    uint32_t* ubits = fbits + nwords;                          // uncovered in either eye (mask)
+
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) ubits[i] = 0u;
+
+    const int mode = a.mode;
+    int wo = w, ho = h;
+    if (mode == CS_MODE_LEFT_RIGHT || mode == CS_MODE_RIGHT_LEFT) wo = 2 * w;
+    if (mode == CS_MODE_TOP_BOTTOM || mode == CS_MODE_BOTTOM_TOP) ho = 2 * h;
+    float* outf = a.stereo + (int64_t)frame * ho * wo * 3;
+    const float* img = a.image + (int64_t)frame * h * w * 3;
+    const int ng = (a.n + a.group - 1) / a.group;
+
+    // the strip of quads this row's pixel centres fall in: largest r <= h - 2 with Y(r) <= y + 0.5
+    const float ys = (float)y + 0.5f;
+    int r = 0;
+    float fy = 0.0f;
+    if (h >= 2) {
+        r = (int)(((double)y + 0.5) * (double)(h - 1) / (double)h);
+        r = max(0, min(r, h - 2));
+        while (r > 0 && mesh_window_y(r, h) > ys) --r;
+        while (r < h - 2 && mesh_window_y(r + 1, h) <= ys) ++r;
+        const float yr = mesh_window_y(r, h), yn = mesh_window_y(r + 1, h);
+        fy = (ys - yr) / (yn - yr);
+    }
+    const float* r0 = img + (int64_t)r * w * 3;
+    const float* r1 = r0 + (int64_t)w * 3;
+
+    for (int eye = 0; eye < 2; ++eye) {
+        int oy = y, ox = 0, ch_lo = 0, ch_hi = 3;
+        bool emit = true;
+        switch (mode) {
+            case CS_MODE_LEFT_RIGHT: ox = eye ? w : 0; break;
+            case CS_MODE_RIGHT_LEFT: ox = eye ? 0 : w; break;
+            case CS_MODE_TOP_BOTTOM: oy = eye ? y + h : y; break;
+            case CS_MODE_BOTTOM_TOP: oy = eye ? y : y + h; break;
+            case CS_MODE_RED_CYAN: if (eye == 0) { ch_lo = 0; ch_hi = 1; } else { ch_lo = 1; ch_hi = 3; } break;
+            case CS_MODE_CYAN_RED: if (eye == 1) { ch_lo = 0; ch_hi = 1; } else { ch_lo = 1; ch_hi = 3; } break;
+            case CS_MODE_LEFT_ONLY: emit = (eye == 0); break;
+            default: emit = (eye == 1); break;
+        }
+        float* orow = outf + ((int64_t)oy * wo + ox) * 3;
+
+        if (a.eye[eye].passthrough) {
+            if (emit)
+                for (int x = threadIdx.x; x < w; x += blockDim.x)
+                    for (int ch = ch_lo; ch < ch_hi; ++ch) orow[x * 3 + ch] = img[((int64_t)y * w + x) * 3 + ch];
+            continue;
+        }
+        __syncthreads();   // the previous eye's readers are done with key / X / N / fbits
+        const bool degenerate = h < 2 || w < 2;   // no triangles at all: nothing is covered
+        const float div_px = (float)a.eye[eye].div_px, sep_px = (float)a.eye[eye].sep_px;
+        if (!degenerate) {
+            const DepthNorm nm = gw_depth_norm(a, frame, eye);
+            const float* d0 = a.depth[eye] + ((int64_t)frame * h + r) * w;
+            for (int x = threadIdx.x; x < w; x += blockDim.x) {
+                float n0, n1;
+                const float q0 = gw_offset(nm, d0[x], a.conv, a.expo, div_px, sep_px, &n0);
+                const float q1 = gw_offset(nm, d0[w + x], a.conv, a.expo, div_px, sep_px, &n1);
+                N0[x] = n0; N1[x] = n1;
+                X0[x] = mesh_window_x((float)x + q0, w);
+                X1[x] = mesh_window_x((float)x + q1, w);
+                key[x] = 0ull;
+            }
+        } else {
+            for (int x = threadIdx.x; x < w; x += blockDim.x) key[x] = 0ull;
+        }
+        __syncthreads();
+
+        // the two edges and edge depths of triangle `pass` of quad x on this scanline
+        auto tri = [&](int x, int pass, float& e1, float& e2, float& n1, float& n2) {
+            const float ed = mesh_edge(X0[x + 1], X1[x], fy), nd = mesh_lerp(N0[x + 1], N1[x], fy);   // the diagonal v10-v01
+            if (pass == 0) { e1 = mesh_edge(X0[x], X1[x], fy); n1 = mesh_lerp(N0[x], N1[x], fy); e2 = ed; n2 = nd; }
+            else { e1 = ed; n1 = nd; e2 = mesh_edge(X0[x + 1], X1[x + 1], fy); n2 = mesh_lerp(N0[x + 1], N1[x + 1], fy); }
+        };
+
+        if (!degenerate) {
+            const unsigned char* kp = a.keep + (((int64_t)eye * ng + frame / a.group) * (h - 1) + r) * (int64_t)(w - 1);
+            for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) {
+                const int kept = kp[x];
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (!((kept >> pass) & 1)) continue;
+                    float e1, e2, n1, n2;
+                    tri(x, pass, e1, e2, n1, n2);
+                    const float lo = fminf(e1, e2), hi = fmaxf(e1, e2);
+                    if (!(lo < hi)) continue;
+                    const float c0 = ceilf(lo - 0.5f), c1 = ceilf(hi - 0.5f) - 1.0f;
+                    if (!(c0 <= (float)(w - 1)) || !(c1 >= 0.0f)) continue;
+                    const int i0 = c0 < 0.0f ? 0 : (int)c0, i1 = c1 > (float)(w - 1) ? w - 1 : (int)c1;
+                    const uint32_t tie = 0xffffffffu - (uint32_t)(pass * (w - 1) + x);
+                    for (int i = i0; i <= i1; ++i) {
+                        const float xs = (float)i + 0.5f;
+                        if (!(lo <= xs && xs < hi)) continue;
+                        const float t = (xs - e1) / (e2 - e1);
+                        const float z = mesh_lerp(n1, n2, t);
+                        uint32_t zo = __float_as_uint(z);
+                        zo = (zo & 0x80000000u) ? ~zo : (zo | 0x80000000u);
+                        atomicMax(&key[i], ((unsigned long long)zo << 32) | tie);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        {   // coverage bitmap, mask
+            const int wpad = nwords << 5;
+            for (int x = threadIdx.x; x < wpad; x += blockDim.x) {
+                const bool f = (x < w) && key[x] != 0ull;
+                const uint32_t b = __ballot_sync(0xffffffffu, f);
+                if ((threadIdx.x & 31) == 0) {
+                    fbits[x >> 5] = b;
+                    const uint32_t valid = (x + 32 <= w) ? 0xffffffffu : ((1u << (w - x)) - 1u);
+                    ubits[x >> 5] |= (~b) & valid;
+                }
+            }
+        }
+        __syncthreads();
+        if (!emit) continue;
+
+        const bool from_left = div_px >= 0.0f;   // SIG:663
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            int sc = x;
+            if (key[x] == 0ull) {     // gap: nearest covered column on the fill side, if there is one
+                sc = -1;
+                int wi = x >> 5;
+                if (from_left) {
+                    uint32_t m = fbits[wi] & (0xffffffffu >> (31 - (x & 31)));
+                    while (true) {
+                        if (m) { sc = (wi << 5) + 31 - __clz(m); break; }
+                        if (--wi < 0) break;
+                        m = fbits[wi];
+                    }
+                } else {
+                    uint32_t m = fbits[wi] & (0xffffffffu << (x & 31));
+                    while (true) {
+                        if (m) { sc = (wi << 5) + __ffs(m) - 1; break; }
+                        if (++wi >= nwords) break;
+                        m = fbits[wi];
+                    }
+                }
+            }
+            if (sc < 0) {
+                for (int ch = ch_lo; ch < ch_hi; ++ch) orow[x * 3 + ch] = 0.0f;    // the cleared colour buffer
+                continue;
+            }
+            const uint32_t order = 0xffffffffu - (uint32_t)(key[sc] & 0xffffffffull);
+            const int pass = order >= (uint32_t)(w - 1) ? 1 : 0, q = (int)order - pass * (w - 1);
+            float e1, e2, n1, n2;
+            tri(q, pass, e1, e2, n1, n2);
+            const float t = (((float)sc + 0.5f) - e1) / (e2 - e1);
+            // vertex pairs of the two edges: a = (v00-v01, v10-v01), b = (v10-v01, v10-v11)
+            const int ta = pass ? q + 1 : q, ba = q, tb = q + 1, bb = pass ? q + 1 : q;
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                const float a1 = mesh_lerp(r0[ta * 3 + ch], r1[ba * 3 + ch], fy);
+                const float a2 = mesh_lerp(r0[tb * 3 + ch], r1[bb * 3 + ch], fy);
+                orow[x * 3 + ch] = mesh_lerp(a1, a2, t);
+            }
+        }
+    }
+    __syncthreads();
+    float* mrow = a.mask + ((int64_t)frame * h + y) * w;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) mrow[x] = ((ubits[x >> 5] >> (x & 31)) & 1u) ? 1.0f : 0.0f;
+}
+
+size_t mesh_keep_bytes(int n, int h, int w) { return (size_t)2 * n * (h > 1 ? h - 1 : 1) * (w > 1 ? w - 1 : 1); }
+
+cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
+    const int nwords = (a.w + 31) >> 5;
+    if (!a.keep || a.group < 1) return cudaErrorInvalidValue;
+    const int ng = (a.n + a.group - 1) / a.group;
+    if (a.h >= 2 && a.w >= 2) {
+        const size_t ksm = (size_t)a.w * 9;
+        if (ksm > 227 * 1024) return cudaErrorInvalidValue;
+        if (ksm > 48 * 1024) cudaFuncSetAttribute(k_mesh_keep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm);
+        prof_begin(K_GPUWARP, s);
+        k_mesh_keep<<<dim3(a.h - 1, ng, 2), 256, ksm, s>>>(a);
+        prof_end(K_GPUWARP, s);
+        count_launch();
+    }
+    const size_t smem = (size_t)a.w * 24 + (size_t)nwords * 8;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_meshwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prof_begin(K_GPUWARP, s);
+    k_meshwarp<<<dim3(a.h, a.n), 256, smem, s>>>(a);
+    prof_end(K_GPUWARP, s);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {

@@ -340,8 +340,9 @@ int cs_stereo_batch_host_progress(const cs_params* p, const float* image, const 
     const size_t dpx = resize ? (size_t)p->depth_h * p->depth_w : px;   // depth frames may have their own size (N1)
     const size_t b_img = px * 3 * 4, b_dep = dpx * c * 4, b_st = (size_t)ho * wo * 3 * 4, b_d = px * 3 * 4, b_m = (size_t)hm * wm * 4;
     const size_t in_frame = b_img + b_dep, out_frame = b_st + 2 * b_d + b_m;
+    const bool gpu_warp = p->fill == CS_FILL_GPU_WARP || p->fill == CS_FILL_GPU_WARP_MESH;
     // chunk: whole GPU-Warp sub-batches (Q9); otherwise ~256 MB of I/O per slot
-    int group = (p->fill == CS_FILL_GPU_WARP && p->group_size > 0) ? (p->group_size < n ? p->group_size : n) : 1;
+    int group = (gpu_warp && p->group_size > 0) ? (p->group_size < n ? p->group_size : n) : 1;
     int chunk = (int)((size_t)256 * 1024 * 1024 / (in_frame + out_frame));
     if (chunk < 1) chunk = 1;
     chunk = (chunk / group) * group;
@@ -361,7 +362,7 @@ int cs_stereo_batch_host_progress(const cs_params* p, const float* image, const 
     if (!is_pinned(mask)) hint_huge_pages(mask, (size_t)n * b_m);
     auto al256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // every CPU technique's depth outputs are exactly k / 255 (wrap quirk Q1): one byte per pixel is enough
-    const bool depth_u8 = compact && p->fill != CS_FILL_GPU_WARP;
+    const bool depth_u8 = compact && !gpu_warp;
     const size_t dsz = depth_u8 ? 1 : 4;
     float lut[256];
     for (int k = 0; k < 256; ++k) lut[k] = (float)k / 255.0f;

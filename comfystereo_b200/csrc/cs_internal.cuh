@@ -234,8 +234,12 @@ struct GpuWarpArgs {
     float expo, conv;
     float* stereo;             // final layout
     float* mask;               // [n][h][w]
+    uint8_t* keep;             // mesh warp only: mesh_keep_bytes(n, h, w) of scratch for the culled topology
 };
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s);
+// forward_warp_mesh (SIG:453-689): same arguments, plus the keep scratch
+size_t mesh_keep_bytes(int n, int h, int w);
+cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s);
 // one channel of each depth output + one byte per mask pixel, for the host transport (cs_host.cu)
 // (depth_u8: the depth outputs are k / 255 -- every CPU technique -- and travel as the byte k)
 cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,

@@ -12,6 +12,8 @@ import torch
 from . import _lib
 from ._lib import CsParams, FILL_KEYS, MODES
 
+GPU_WARP_KEYS = ('gpu_warp', 'gpu_warp_mesh')
+
 FILL_NAME_TO_KEY = {  # the node's dropdown labels -> dispatch keys, GS:88-100
     'GPU Warp (Fast)': 'gpu_warp',
     'No fill': 'none',
@@ -87,7 +89,7 @@ def default_chunk(p, n, h, w):
     """Frames per kernel sequence: about sixteen 1080p frames' worth of pixels.  Measured on B200 (chunk sweep in
     profiles/): fewer, larger launches (fewer partial waves and launch gaps) matter more than keeping the ~26 B/px of
     scratch inside L2 -- 4 / 8 / 16 frames per sequence: 3.73 / 3.56 / 3.46 ms per 16 frames of 1080p Polylines Sharp."""
-    group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
+    group = p.group_size if (FILL_KEYS[p.fill] in GPU_WARP_KEYS and p.group_size > 0) else 1
     group = min(group, n)
     target = max(1, int(33.6e6 // (h * w)))
     chunk = max(group, (target // group) * group)
@@ -225,6 +227,23 @@ def warp_fill_device(image_rgbx, depth, fill_key, divergence, separation, expone
     return out
 
 
+def forward_warp_device(image, depth, div_px, sep_px, exponent, convergence, mesh=False):
+    """cs_forward_warp / cs_forward_warp_mesh (forward_warp_gpu SIG:277-450 / forward_warp_mesh SIG:453-689) for ONE eye:
+    image [n,h,w,3] float32 CUDA, depth [n,h,w] as given.  Returns (warped [n,h,w,3], mask float32 [n,h,w])."""
+    n, h, w = depth.shape
+    lib = _lib.lib()
+    nb = lib.cs_forward_warp_mesh_scratch_bytes(n, h, w) if mesh else 32 * n
+    scratch = torch.empty(nb, dtype=torch.uint8, device=depth.device)
+    warped = torch.empty((n, h, w, 3), dtype=torch.float32, device=depth.device)
+    mask = torch.empty((n, h, w), dtype=torch.float32, device=depth.device)
+    fn = lib.cs_forward_warp_mesh if mesh else lib.cs_forward_warp
+    with torch.cuda.device(depth.device):
+        _lib.check(fn(image.contiguous().data_ptr(), depth.contiguous().data_ptr(), n, h, w, float(div_px), float(sep_px),
+                      float(exponent), float(convergence), warped.data_ptr(), mask.data_ptr(), scratch.data_ptr(), nb,
+                      _stream_ptr(depth.device)))
+    return warped, mask
+
+
 def compose_device(left_rgbx, right_rgbx, mode):
     """cs_compose: two [n,h,w,4] uint8 eyes -> (stereo [n,ho,wo,3] float32 = u8 / 255, mask [n,ho,wo])."""
     n, h, w, _ = left_rgbx.shape
@@ -273,7 +292,7 @@ def stereo_batch_multi_gpu(image, depth, p, devices, resize_depth=False, progres
             torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
             torch.empty(d_shape, dtype=torch.float32, pin_memory=pin),
             torch.empty(m_shape, dtype=torch.float32, pin_memory=pin))
-    group = p.group_size if (FILL_KEYS[p.fill] == 'gpu_warp' and p.group_size > 0) else 1
+    group = p.group_size if (FILL_KEYS[p.fill] in GPU_WARP_KEYS and p.group_size > 0) else 1
     lib = _lib.lib()
     errors = []
     done = [0]          # frames finished on any device; the caller's thread forwards it to `progress`

@@ -2,14 +2,25 @@
 
     create_stereoimages(...)      SIG:1422-1574   CPU techniques, one frame, returns PIL images
     create_stereoimages_gpu(...)  SIG:1005-1128   'GPU Warp (Fast)', a sub-batch, returns tensors
+    forward_warp_gpu(...)         SIG:277-450     one eye of it, the scatter warp
+    forward_warp_mesh(...)        SIG:453-689     one eye of it, the mesh warp the reference uses when moderngl imports
 
 Same names, argument order, defaults, return shapes and exceptions; the work is done by the
 sm_100a kernels behind the C ABI (comfystereo_b200/engine.py).  There is no CPU implementation
 here: without a B200 and the built library these functions raise.
 """
+import os
+
 import torch
 
 from . import engine
+
+# The reference picks the warp of 'GPU Warp (Fast)' from this module flag (SIG:29-36, 1068-1071): forward_warp_mesh when
+# moderngl imported, forward_warp_gpu otherwise.  Here nothing depends on OpenGL, so it is a plain switch: False (the
+# default) = the scatter warp, bit-exact against the reference; True = the mesh warp, a software rasteriser whose
+# coverage/interpolation rule set is fixed and documented (DESIGN.md section 9) because OpenGL's is not.
+# COMFYSTEREO_GPU_WARP=mesh sets it at import.
+MODERNGL_AVAILABLE = os.environ.get("COMFYSTEREO_GPU_WARP", "scatter").lower() == "mesh"
 
 _CPU_FILLS = ('none', 'naive', 'naive_interpolating', 'polylines_soft', 'polylines_sharp', 'inverse',
               'hybrid_edge', 'none_post', 'inverse_post', 'hybrid_edge_plus')
@@ -144,12 +155,46 @@ def _create_stereoimages_arrays(original_image, depthmap, divergence, separation
     return stereo_images, depth_image(d)
 
 
+def _forward_warp(image_tensor, depth_tensor, divergence_px, separation_px, stereo_offset_exponent, convergence_point, mesh):
+    dev = _device()
+    img = image_tensor.to(dev, torch.float32).permute(0, 2, 3, 1).contiguous()
+    if img.shape[3] != 3:
+        raise NotImplementedError("the warp kernels take 3-channel images")
+    dep = depth_tensor.to(dev, torch.float32).contiguous()
+    warped, mask = engine.forward_warp_device(img, dep, divergence_px, separation_px, stereo_offset_exponent,
+                                              convergence_point, mesh=mesh)
+    return warped.permute(0, 3, 1, 2), mask > 0.5
+
+
+def forward_warp_gpu(image_tensor, depth_tensor, divergence_px, separation_px, stereo_offset_exponent,
+                     convergence_point=0.5, max_stretch=8):
+    """SIG:277-450.  image_tensor [B,3,H,W] (0..1), depth_tensor [B,H,W] (0..1 or 0..255; /255 when ANY frame's max > 1).
+    Returns (warped [B,3,H,W], unfilled bool [B,H,W]) on the CUDA device.  max_stretch is the reference's scatter round
+    count; only its default 8 is implemented."""
+    if max_stretch != 8:
+        raise NotImplementedError("forward_warp_gpu: max_stretch is fixed at the reference's default 8")
+    return _forward_warp(image_tensor, depth_tensor, divergence_px, separation_px, stereo_offset_exponent,
+                         convergence_point, False)
+
+
+def forward_warp_mesh(image_tensor, depth_tensor, divergence_px, separation_px, stereo_offset_exponent,
+                      convergence_point=0.5, gradient_threshold=1.5, max_stretch=8):
+    """SIG:453-689, rasterised in software with the rule set of DESIGN.md section 9.  Same shapes as forward_warp_gpu;
+    the mask is the pre-fill gap map.  gradient_threshold is fixed at the reference's default 1.5 (max_stretch is unused
+    there too)."""
+    if gradient_threshold != 1.5:
+        raise NotImplementedError("forward_warp_mesh: gradient_threshold is fixed at the reference's default 1.5")
+    return _forward_warp(image_tensor, depth_tensor, divergence_px, separation_px, stereo_offset_exponent,
+                         convergence_point, True)
+
+
 def create_stereoimages_gpu(image_tensor, depth_tensor, divergence, separation=0.0, modes=None,
                             stereo_balance=0.0, stereo_offset_exponent=1.0, convergence_point=0.5,
                             depth_blur_strength=0.0, depth_blur_edge_threshold=6.0,
                             direction_aware_depth_blur=False, depth_blur_falloff=1.0,
                             depth_blur_vert_smooth=0):
-    """A sub-batch through 'GPU Warp (Fast)'.  image_tensor [B,3,H,W], depth_tensor [B,H,W].
+    """A sub-batch through 'GPU Warp (Fast)' (the scatter warp, or the mesh warp when MODERNGL_AVAILABLE is set).
+    image_tensor [B,3,H,W], depth_tensor [B,H,W].
     Returns (list of [B,3,Ho,Wo] tensors, left_depth [B,H,W], right_depth [B,H,W], mask bool [B,H,W])
     on the CUDA device, like the reference does when CUDA is available."""
     if modes is None:
@@ -167,7 +212,7 @@ def create_stereoimages_gpu(image_tensor, depth_tensor, divergence, separation=0
     dm = depth_tensor.to(dev, torch.float32).reshape(b, h, w, 1).contiguous()
     results, left, right, mask = [], None, None, None
     for mode in modes:
-        p = engine.make_params('gpu_warp', mode, divergence, separation, stereo_balance, convergence_point,
+        p = engine.make_params('gpu_warp_mesh' if MODERNGL_AVAILABLE else 'gpu_warp', mode, divergence, separation, stereo_balance, convergence_point,
                                stereo_offset_exponent, direction_aware_depth_blur, depth_blur_strength,
                                depth_blur_edge_threshold, depth_blur_falloff, depth_blur_vert_smooth,
                                group_size=b)

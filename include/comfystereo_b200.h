@@ -58,7 +58,12 @@ typedef enum cs_fill {
      * (GS:97-99) but no longer lists: */
     CS_FILL_NONE_POST = 8,       /* 'none_post'         SIG:1804-1818: naive mapping + np.interp row fill */
     CS_FILL_INVERSE_POST = 9,    /* 'inverse_post'      SIG:1820-1833: reverse projection + np.interp row fill */
-    CS_FILL_HYBRID_EDGE_PLUS = 10 /* 'hybrid_edge_plus' SIG:1778-1802: hybrid edge, black pixels from polylines_soft */
+    CS_FILL_HYBRID_EDGE_PLUS = 10, /* 'hybrid_edge_plus' SIG:1778-1802: hybrid edge, black pixels from polylines_soft */
+    /* 'GPU Warp (Fast)' on a host with ModernGL: forward_warp_mesh, SIG:453-689 (selected at SIG:1068-1071).  The
+     * reference rasterises the mesh with OpenGL, whose fragment coverage and interpolation rounding are
+     * implementation-defined; this is a software rasteriser with a fixed rule set (oracle/stereo_oracle.c:orc_mesh_raster,
+     * bit-exact against it).  Everything else -- blur, sub-batch coupling, composition, mask -- is CS_FILL_GPU_WARP's. */
+    CS_FILL_GPU_WARP_MESH = 11
 } cs_fill;
 
 /* composition modes, SIG:1543-1562 / SIG:1093-1120 */
@@ -160,6 +165,16 @@ CS_API size_t cs_warp_fill_scratch_bytes(int n, int h, int w);
 CS_API int cs_forward_warp(const float *image, const float *depth, int n, int h, int w, double div_px,
                     double sep_px, double exponent, double convergence, float *warped, float *mask,
                     void *scratch, size_t scratch_bytes, void *stream);
+
+/* The same for the ModernGL variant: replaces forward_warp_mesh(image, depth, divergence_px, separation_px,
+ * stereo_offset_exponent, convergence_point), SIG:453-689 -- the mesh of per-pixel vertices, culled with the
+ * reference's gradient rule over the whole batch (SIG:522-537), drawn by a software rasteriser with a fixed rule set
+ * (see CS_FILL_GPU_WARP_MESH), gaps smeared from the eye's fill side (SIG:655-683).  Same argument meaning and layouts
+ * as cs_forward_warp; scratch: cs_forward_warp_mesh_scratch_bytes(n, h, w). */
+CS_API int cs_forward_warp_mesh(const float *image, const float *depth, int n, int h, int w, double div_px,
+                    double sep_px, double exponent, double convergence, float *warped, float *mask,
+                    void *scratch, size_t scratch_bytes, void *stream);
+CS_API size_t cs_forward_warp_mesh_scratch_bytes(int n, int h, int w);
 
 /* O1 input side.  Replaces SIG:1506-1508: clip(x*255, 0, 255).astype(uint8) (truncation). */
 CS_API int cs_quantize_image(const float *image, int n, int h, int w, uint8_t *image_u8, void *stream);

@@ -225,6 +225,36 @@ def gpuwarp_eye(img_chw, depth01, div_px, sep_px, expo, conv):
     return out, mask.astype(bool)
 
 
+def meshwarp_batch(img_bchw, depth01_bhw, div_px, sep_px, expo, conv):
+    """forward_warp_mesh (SIG:453-689) for a whole sub-batch; depth01 already /255 (SIG:487-489 handled by the caller).
+    The triangle culling is batch-wide (SIG:522-537: kept when it passes in ANY frame), the rasterisation is
+    orc_mesh_raster's rule set -- OpenGL's own is implementation-defined, so parity with the reference is UNPINNED here."""
+    img = _c(img_bchw, np.float32)
+    d = _c(depth01_bhw, np.float32)
+    B, H, W = d.shape
+    f = lambda v: ctypes.c_float(np.float32(v))
+    nd = np.empty((B, H, W), np.float32)
+    po = np.empty((B, H, W), np.float32)
+    for b in range(B):
+        lib().orc_mesh_offsets(_p(d[b]), H, W, f(div_px), f(sep_px), f(expo), f(conv), _p(nd[b]), _p(po[b]))
+    out = np.zeros_like(img)
+    mask = np.ones((B, H, W), np.uint8)
+    if H < 2 or W < 2:      # no triangles: nothing is covered and there is nothing to smear from
+        return out, mask.astype(bool)
+    o00, o10, o01, o11 = po[:, :-1, :-1], po[:, :-1, 1:], po[:, 1:, :-1], po[:, 1:, 1:]
+    thr = np.float32(1.5)
+    with np.errstate(invalid='ignore'):
+        diag = np.abs(o10 - o01)
+        ka = np.maximum(np.maximum(np.abs(o00 - o10), np.abs(o00 - o01)), diag) < thr
+        kb = np.maximum(np.maximum(np.abs(o11 - o10), np.abs(o11 - o01)), diag) < thr
+    keep_a = _c(ka.any(axis=0), np.uint8)
+    keep_b = _c(kb.any(axis=0), np.uint8)
+    for b in range(B):
+        lib().orc_mesh_raster(_p(img[b]), _p(nd[b]), _p(po[b]), _p(keep_a), _p(keep_b), H, W,
+                              1 if np.float32(div_px) >= 0 else 0, _p(out[b]), _p(mask[b]))
+    return out, mask.astype(bool)
+
+
 # ------------------------------------------------------------------ pipeline glue
 def apply_stereo_divergence(img_u8, depth, divergence, separation, expo, fill, conv):
     """SIG:1576-1620."""
@@ -301,8 +331,8 @@ def create_stereoimages_gpu(image_bchw, depth_bhw, divergence, separation=0.0, m
                             stereo_balance=0.0, stereo_offset_exponent=1.0, convergence_point=0.5,
                             depth_blur_strength=0.0, depth_blur_edge_threshold=6.0,
                             direction_aware_depth_blur=False, depth_blur_falloff=1.0,
-                            depth_blur_vert_smooth=0, blur_override=None):
-    """SIG:1005-1128 with warp_fn = forward_warp_gpu (moderngl absent), one sub-batch."""
+                            depth_blur_vert_smooth=0, blur_override=None, mesh=False):
+    """SIG:1005-1128, one sub-batch; warp_fn = forward_warp_gpu (moderngl absent) or, with mesh=True, forward_warp_mesh."""
     if modes is None:
         modes = ['left-right']
     if not isinstance(modes, list):
@@ -329,6 +359,8 @@ def create_stereoimages_gpu(image_bchw, depth_bhw, divergence, separation=0.0, m
         d = depth_b
         if (d.reshape(B, -1).max(axis=1) > 1.0).any():  # SIG:314-316, whole sub-batch
             d = d / np.float32(255.0)
+        if mesh:
+            return meshwarp_batch(img, d, div_px, sp, stereo_offset_exponent, convergence_point)
         outs, masks = [], []
         for b in range(B):
             o, m = gpuwarp_eye(img[b], d[b], div_px, sp, stereo_offset_exponent, convergence_point)
@@ -373,7 +405,7 @@ def node_generate(image, depth_map, divergence=4.5, separation=0.0, modes="left-
                   stereo_balance=0.0, convergence_point=0.5, stereo_offset_exponent=2.0,
                   fill_technique='GPU Warp (Fast)', depth_blur_edge_threshold=20.0,
                   depth_blur_strength=20.0, depth_map_blur=True, depth_blur_falloff=1.0,
-                  depth_blur_vert_smooth=0, batch_size=4, blur_override=None):
+                  depth_blur_vert_smooth=0, batch_size=4, blur_override=None, mesh=False):
     """StereoImageNode.generate (GS:79-353) on numpy arrays: image [N,H,W,3], depth [N,H,W,C].
     Returns (stereo [N,Ho,Wo,3], depth_left [N,H,W,3], depth_right [N,H,W,3], mask [N,Hm,Wm]) float32."""
     image = np.asarray(image, np.float32)
@@ -397,7 +429,7 @@ def node_generate(image, depth_map, divergence=4.5, separation=0.0, modes="left-
                 img, dm, divergence, separation, [modes], stereo_balance, stereo_offset_exponent,
                 convergence_point, depth_blur_strength, depth_blur_edge_threshold, depth_map_blur,
                 depth_blur_falloff, depth_blur_vert_smooth,
-                blur_override=None if blur_override is None else tuple(b[s:s + gb] for b in blur_override))
+                blur_override=None if blur_override is None else tuple(b[s:s + gb] for b in blur_override), mesh=mesh)
             st.append(res[0].transpose(0, 2, 3, 1))
             dls.append(np.repeat(np.clip(dl, 0, 1)[..., None], 3, axis=-1))
             drs.append(np.repeat(np.clip(dr, 0, 1)[..., None], 3, axis=-1))
