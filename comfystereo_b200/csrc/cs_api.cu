@@ -291,7 +291,7 @@ size_t cs_workspace_bytes(const cs_params* p, int chunk, int h, int w) {
     return carve(p, chunk, h, w, nullptr).total;
 }
 
-void cs_set_test_flags(int flags) { g_test_flags.store(flags); }
+void cs_set_test_flags(int flags) { g_test_flags.store(flags); set_blur_test_flags((flags >> 5) & 1); }
 
 int cs_profile_kernel_count(void) { return K_COUNT; }
 const char* cs_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }

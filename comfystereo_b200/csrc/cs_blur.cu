@@ -17,6 +17,9 @@
 // depth scratch and, for CPU techniques, 24 B of depth outputs (streamed, evict-first).
 #include "cs_internal.cuh"
 
+#include <atomic>
+#include <cmath>
+
 namespace cs {
 
 struct BlurLut {
@@ -148,6 +151,109 @@ __global__ void __launch_bounds__(256) k_edge_dist(const float* __restrict__ gra
             const int pn = mr ? (wi << 5) + __ffs(mr) - 1 : nextpos[pass * nwords + wi];
             const int d = min(min(x - pl, pn - x), far);
             (pass ? orr : ol)[x] = (uint8_t)d;
+        }
+    }
+}
+
+// The same for rows whose width is a multiple of 4 (every video format): four pixels per thread from 128-bit loads, the
+// IEEE division of SIG:1217 replaced by the threshold it is equivalent to (division by a positive constant is monotone:
+// fl(|g| / edge_div) > 0.5  <=>  |g| >= thr, thr found on the host), the two masks assembled from nibbles with three
+// shuffles, four distances per 32-bit store.  ~45 instructions per pixel instead of ~160.
+__global__ void __launch_bounds__(256) k_edge_dist4(const float* __restrict__ gray, const FrameStats* __restrict__ st,
+                                                    int scale_mode, int group, int n, int h, int w, float thr, int radius,
+                                                    uint8_t* __restrict__ dist_l, uint8_t* __restrict__ dist_r) {
+    extern __shared__ uint32_t s_bits[];  // [2][nwords] masks, [2][nwords] prevpos, [2][nwords] nextpos
+    const int y = blockIdx.x, frame = blockIdx.y;
+    const int nwords = (w + 31) >> 5;
+    uint32_t* bl = s_bits;
+    uint32_t* br = s_bits + nwords;
+    const float scale = frame_scale(st, frame, scale_mode, group, n);
+    const float* base = gray + (int64_t)frame * h * w;
+    const float* rows[3] = {(y > 0) ? base + (int64_t)(y - 1) * w : nullptr, base + (int64_t)y * w,
+                            (y + 1 < h) ? base + (int64_t)(y + 1) * w : nullptr};
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    for (int xb = wid * 128; xb < w; xb += 4 * blockDim.x) {
+        const int x4 = xb + 4 * lane;
+        const bool act = x4 < w;
+        float g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (!rows[r]) continue;                         // zero padding above / below: no terms (block-uniform)
+            float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float l = 0.0f, rr = 0.0f;
+            if (act) {
+                c = *reinterpret_cast<const float4*>(rows[r] + x4);
+                if (x4 > 0) l = rows[r][x4 - 1];
+                if (x4 + 4 < w) rr = rows[r][x4 + 4];
+                if (scale != 1.0f) { c.x *= scale; c.y *= scale; c.z *= scale; c.w *= scale; l *= scale; rr *= scale; }
+            }
+            const float k = (r == 1) ? 2.0f : 1.0f;
+            const float v[6] = {l, c.x, c.y, c.z, c.w, rr};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                g[j] = fmaf(-k, v[j], g[j]);
+                g[j] = fmaf(k, v[j + 2], g[j]);
+            }
+        }
+        uint32_t nl = 0, nr = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool strong = fabsf(g[j]) >= thr;
+            nl |= (uint32_t)(strong && g[j] > 0.0f) << j;
+            nr |= (uint32_t)(strong && g[j] < 0.0f) << j;
+        }
+        const int sh = 4 * (lane & 7);
+        uint32_t vl = nl << sh, vr = nr << sh;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            vl |= __shfl_xor_sync(0xffffffffu, vl, o);
+            vr |= __shfl_xor_sync(0xffffffffu, vr, o);
+        }
+        const int wi = (xb >> 5) + (lane >> 3);
+        if ((lane & 7) == 0 && wi < nwords) { bl[wi] = vl; br[wi] = vr; }
+    }
+    __syncthreads();
+
+    const int far = radius + 1;
+    int* prevpos = reinterpret_cast<int*>(s_bits + 2 * nwords);   // [2][nwords]
+    int* nextpos = prevpos + 2 * nwords;                          // [2][nwords]
+    const int kwords = (radius >> 5) + 1;
+    for (int t = threadIdx.x; t < 2 * nwords; t += blockDim.x) {
+        const int pass = t >= nwords, wi = pass ? t - nwords : t;
+        const uint32_t* bits = pass ? br : bl;
+        int pp = -(1 << 28), np = 1 << 28;
+        for (int k = 1; k <= kwords && wi - k >= 0; ++k) {
+            uint32_t q = bits[wi - k];
+            if (q) { pp = ((wi - k) << 5) + 31 - __clz(q); break; }
+        }
+        for (int k = 1; k <= kwords && wi + k < nwords; ++k) {
+            uint32_t q = bits[wi + k];
+            if (q) { np = ((wi + k) << 5) + __ffs(q) - 1; break; }
+        }
+        prevpos[t] = pp;
+        nextpos[t] = np;
+    }
+    __syncthreads();
+    uint32_t* ol = reinterpret_cast<uint32_t*>(dist_l + ((int64_t)frame * h + y) * w);
+    uint32_t* orr = reinterpret_cast<uint32_t*>(dist_r + ((int64_t)frame * h + y) * w);
+    for (int x4 = 4 * threadIdx.x; x4 < w; x4 += 4 * blockDim.x) {
+        const int wi = x4 >> 5, b0 = x4 & 31, wbase = wi << 5;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t word = (pass ? br : bl)[wi];
+            const int pp = prevpos[pass * nwords + wi], np = nextpos[pass * nwords + wi];
+            uint32_t pack = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = b0 + j, x = x4 + j;
+                const uint32_t ml = word & (0xffffffffu >> (31 - b));
+                const uint32_t mr = word & (0xffffffffu << b);
+                const int pl = ml ? wbase + 31 - __clz(ml) : pp;
+                const int pn = mr ? wbase + __ffs(mr) - 1 : np;
+                pack |= (uint32_t)min(min(x - pl, pn - x), far) << (8 * j);
+            }
+            (pass ? orr : ol)[x4 >> 2] = pack;
         }
     }
 }
@@ -499,6 +605,9 @@ static void build_lut(BlurLut& lut, int radius, float falloff, bool numpy_pow = 
     }
 }
 
+static std::atomic<int> g_blur_test_flags{0};   // bit 0: the scalar k_edge_dist even where the 4-pixel form applies (tests)
+void set_blur_test_flags(int flags) { g_blur_test_flags.store(flags); }
+
 cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, int group, int n, int h,
                         int w, const cs_params& p, float* blur_l, float* blur_r, uint8_t* dist,
                         float* depth_l_out, float* depth_r_out, cudaStream_t s) {
@@ -514,7 +623,15 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     if (np_flavor)
         k_edge_dist<true><<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
             gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
-    else
+    else if (w % 4 == 0 && edge_div > 0.0f && std::isfinite(edge_div) && !(g_blur_test_flags.load() & 1)) {
+        // smallest float32 whose quotient by edge_div rounds above 0.5 (the division is monotone in its numerator)
+        float thr = 0.5f * edge_div;
+        while (thr > 0.0f && thr / edge_div > 0.5f) thr = nextafterf(thr, 0.0f);
+        while (!(thr / edge_div > 0.5f)) thr = nextafterf(thr, INFINITY);
+        // (64- to 256-thread CTAs measure the same; wider ones wait longer at the two barriers)
+        k_edge_dist4<<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
+            gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, thr, radius, dist_l, dist_r);
+    } else
         k_edge_dist<false><<<dim3(h, n), 256, 6 * nwords * sizeof(uint32_t), s>>>(
             gray, stats, scale_mode, group < 1 ? 1 : group, n, h, w, edge_div, radius, dist_l, dist_r);
     prof_end(K_EDGE_DIST, s);

@@ -201,6 +201,7 @@ cudaError_t launch_prepare(const float* image, const float* depth, int n, int h,
 // scale_mode 0: input already 0..255; 1: x255 when the frame's gray max <= 1 (SIG:1475);
 //            2: same test over the frame's sub-batch of `group` frames (SIG:1045)
 // depth_l_out/depth_r_out (optional): the CPU-technique depth outputs (wrap quirk Q1), [n][h][w][3]
+void set_blur_test_flags(int flags);   // bit 0: scalar k_edge_dist (tests)
 cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, int group,
                         int n, int h, int w, const cs_params& p, float* blur_l, float* blur_r,
                         uint8_t* dist, float* depth_l_out, float* depth_r_out, cudaStream_t s);

@@ -245,6 +245,7 @@ CS_API int cs_profile_collect(double *ms, long long *launches);
 /* Test hook.  bit 0: Polylines replays EVERY row with the exact sequential sweep.
  * bit 2: Polylines uses 64-column tiles even when a whole row fits one CTA.  bit 3: every Polylines column through the
  * FP64 exact path.  bit 4: Polylines writes RGBX8 eyes and k_compose composes them (instead of composing in the sweep).
+ * bit 5: the blur's edge-distance pass one pixel per thread with the IEEE division, even where the 4-pixel form applies.
  * bits 8-15: warps per Polylines CTA (0 = choose). */
 CS_API void cs_set_test_flags(int flags);
 

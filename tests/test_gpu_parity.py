@@ -64,6 +64,34 @@ def test_blur_stage(gu, oracle, spec):
     assert mm[0, 0] == L.min() and mm[0, 1] == L.max() and mm[0, 2] == R.min() and mm[0, 3] == R.max()
 
 
+@pytest.mark.parametrize("w", [4, 8, 36, 132, 1920])
+def test_edge_distance_vector_and_scalar_forms_agree(gu, oracle, w):
+    """Rows whose width is a multiple of 4 take k_edge_dist4 (threshold compare instead of the IEEE division, four pixels
+    per thread); test flag 32 forces the one-pixel form.  Same blur bit for bit -- on integer depth, where |g| / (10 thr)
+    lands EXACTLY on 0.5 for many pixels, and on noise -- and equal to the oracle."""
+    from comfystereo_b200 import _lib
+    rng = np.random.default_rng(w)
+    h = 37
+    for kind in range(3):
+        if kind == 0:
+            d = rng.integers(0, 256, (2, h, w)).astype(np.float32)                 # g is an integer: exact ties at thr 3, 6
+        elif kind == 1:
+            d = (rng.random((2, h, w), dtype=np.float32) * np.float32(255))
+        else:
+            d = np.round(syn.make_depth(2, h, w, "scene", seed=w)[..., 0] * 255).astype(np.float32)
+        for strength, thr, falloff, vert in ((9.0, 6.0, 2.0, 2), (33.0, 3.0, 1.0, 0), (5.5, 0.05, 0.5, 6), (64.0, 25.5, 2.0, 1)):
+            fast = gu.blur(d, strength, thr, falloff, vert)
+            _lib.lib().cs_set_test_flags(32)
+            try:
+                slow = gu.blur(d, strength, thr, falloff, vert)
+            finally:
+                _lib.lib().cs_set_test_flags(0)
+            for a, b in zip(fast, slow):
+                assert np.array_equal(a, b), (w, kind, strength, thr)
+            ol, orr = oracle.blur(d[0], strength, thr, falloff, vert)
+            assert np.array_equal(fast[0][0], ol) and np.array_equal(fast[1][0], orr)
+
+
 @pytest.mark.parametrize("case", [(96, 640, 'scene', 200, 60, 4.0, 15), (96, 640, 'scene', 100.5, 0.1, 0.5, 3),
                                   (40, 24, 'scene', 33, 20, 2.0, 6), (64, 300, 'steps', 1.0, 20, 1.0, 0),
                                   (64, 300, 'scene', 0.7, 20, 2.0, 2), (64, 300, 'noise', 1.5, 5, 3.0, 1),
