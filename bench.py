@@ -393,7 +393,16 @@ def main():
                 a1.record()
                 a1.synchronize()
                 ts.append(a0.elapsed_time(a1) * 1e3)
-            latency[name] = {"median_us": float(np.median(ts)), "min_us": float(np.min(ts))}
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(30):
+                engine.stereo_batch_device(li, ld, lp, out=lo)
+            b1.record()
+            b1.synchronize()
+            latency[name] = {"median_us": float(np.median(ts)), "min_us": float(np.min(ts)),
+                             "back_to_back_us": float(b0.elapsed_time(b1) * 1e3 / 30),
+                             "note": "one call, synchronised each time (median/min) and 30 calls queued back to back; repeated "
+                                     "identical calls replay a CUDA graph (COMFYSTEREO_GRAPHS=0: direct launches)"}
 
     # ---- end to end through the node with host tensors
     e2e = None

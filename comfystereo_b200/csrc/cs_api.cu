@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -255,6 +256,60 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
 }
 
 static std::atomic<int> g_test_flags{0};
+
+// ---- CUDA-graph replay of small repeated jobs ------------------------------------------------------
+struct GraphKey {
+    cs_params params;
+    const void* ptr[7];
+    size_t workspace_bytes;
+    int n, h, w, c, flags, device;
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    long long launches;
+    bool failed;
+};
+constexpr size_t kGraphMaxPixels = (size_t)2 * 1920 * 1080;   // beyond two HD frames the kernels dwarf the launches
+constexpr size_t kGraphEntries = 16;
+static std::mutex g_graph_mu;
+static std::vector<GraphEntry> g_graphs;       // most recently used last
+static std::vector<cudaStream_t> g_cap_streams;
+static bool graphs_enabled() {
+    static const bool on = [] { const char* e = getenv("COMFYSTEREO_GRAPHS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static GraphEntry* graph_lookup(const GraphKey& k) {
+    for (size_t i = g_graphs.size(); i-- > 0;)
+        if (memcmp(&g_graphs[i].key, &k, sizeof(k)) == 0) {
+            if (i + 1 != g_graphs.size()) { GraphEntry e = g_graphs[i]; g_graphs.erase(g_graphs.begin() + i); g_graphs.push_back(e); }
+            return &g_graphs.back();
+        }
+    return nullptr;
+}
+static void graph_insert(const GraphKey& k) {
+    if (g_graphs.size() >= kGraphEntries) {
+        if (g_graphs.front().exec) cudaGraphExecDestroy(g_graphs.front().exec);
+        g_graphs.erase(g_graphs.begin());
+    }
+    GraphEntry e;
+    e.key = k; e.exec = nullptr; e.launches = 0; e.failed = false;
+    g_graphs.push_back(e);
+}
+static cudaStream_t graph_capture_stream(int device) {   // capture cannot start on the legacy default stream: a private one per device
+    if (device < 0) return nullptr;
+    if ((size_t)device >= g_cap_streams.size()) g_cap_streams.resize(device + 1, nullptr);
+    if (!g_cap_streams[device] && cudaStreamCreateWithFlags(&g_cap_streams[device], cudaStreamNonBlocking) != cudaSuccess)
+        g_cap_streams[device] = nullptr;
+    return g_cap_streams[device];
+}
+void release_graphs() {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    for (auto& e : g_graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    g_graphs.clear();
+}
+
 
 }  // namespace cs
 
@@ -515,17 +570,64 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     int ho, wo, hm, wm;
     cs_output_dims(p, h, w, &ho, &wo, &hm, &wm);
     cudaStream_t s = (cudaStream_t)stream;
-    for (int f0 = 0; f0 < n; f0 += chunk) {
-        const int m = (n - f0 < chunk) ? n - f0 : chunk;
-        Workspace ws = carve(p, m, h, w, workspace);
-        const size_t px = (size_t)h * w;
-        const size_t dpx = needs_resize(p, h, w) ? (size_t)p->depth_h * p->depth_w : px;
-        rc = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * dpx * c, m, h, w, c,
-                       stereo + (size_t)f0 * ho * wo * 3, depth_l + (size_t)f0 * px * 3, depth_r + (size_t)f0 * px * 3,
-                       mask + (size_t)f0 * hm * wm, ws, g_test_flags.load(), s);
-        if (rc) return rc;
+    auto enqueue = [&](cudaStream_t q) -> int {
+        for (int f0 = 0; f0 < n; f0 += chunk) {
+            const int m = (n - f0 < chunk) ? n - f0 : chunk;
+            Workspace ws = carve(p, m, h, w, workspace);
+            const size_t px = (size_t)h * w;
+            const size_t dpx = needs_resize(p, h, w) ? (size_t)p->depth_h * p->depth_w : px;
+            int r = run_chunk(p, image + (size_t)f0 * px * 3, depth + (size_t)f0 * dpx * c, m, h, w, c,
+                              stereo + (size_t)f0 * ho * wo * 3, depth_l + (size_t)f0 * px * 3, depth_r + (size_t)f0 * px * 3,
+                              mask + (size_t)f0 * hm * wm, ws, g_test_flags.load(), q);
+            if (r) return r;
+        }
+        return CS_OK;
+    };
+    // Small jobs (a frame or two) are bound by launch latency, not by the kernels: the second identical call -- same
+    // buffers, same parameters, what a streaming caller that reuses its tensors makes -- is captured into a CUDA graph
+    // and every later one replays it with a single launch.
+    if (graphs_enabled() && (size_t)n * h * w <= kGraphMaxPixels && !g_prof_on.load(std::memory_order_relaxed)) {
+        GraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.params = *p;
+        key.ptr[0] = image; key.ptr[1] = depth; key.ptr[2] = stereo; key.ptr[3] = depth_l; key.ptr[4] = depth_r;
+        key.ptr[5] = mask; key.ptr[6] = workspace;
+        key.workspace_bytes = workspace_bytes;
+        key.n = n; key.h = h; key.w = w; key.c = c; key.flags = g_test_flags.load();
+        cudaGetDevice(&key.device);
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        GraphEntry* e = graph_lookup(key);
+        if (e && e->exec) {
+            CS_CUDA(cudaGraphLaunch(e->exec, s), "cudaGraphLaunch");
+            g_launches.fetch_add(e->launches, std::memory_order_relaxed);
+            return CS_OK;
+        }
+        if (e && !e->failed) {
+            cudaStream_t cap = graph_capture_stream(key.device);
+            cudaGraph_t graph = nullptr;
+            if (cap && cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                const long long before = g_launches.load();
+                const int r = enqueue(cap);
+                const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+                const long long captured = g_launches.exchange(before) - before;   // nothing has run yet
+                if (r == CS_OK && ce == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
+                    e->launches = captured;
+                    cudaGraphDestroy(graph);
+                    CS_CUDA(cudaGraphLaunch(e->exec, s), "cudaGraphLaunch");
+                    g_launches.fetch_add(e->launches, std::memory_order_relaxed);
+                    return CS_OK;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                e->exec = nullptr;
+                (void)cudaGetLastError();
+            }
+            e->failed = true;        // this configuration does not capture: launch it directly from now on
+        } else if (!e) {
+            graph_insert(key);
+        }
     }
-    return CS_OK;
+    return enqueue(s);
 }
 
 int cs_polylines_status(const cs_params* p, int chunk, int h, int w, const void* workspace, int* status_out, int* flagged_rows) {

@@ -312,6 +312,7 @@ void cs_host_release(void) {
         std::lock_guard<std::mutex> lk(g_mu[i]);
         ctx_free(g_ctx[i]);
     }
+    cs::release_graphs();
 }
 
 int cs_stereo_batch_host(const cs_params* p, const float* image, const float* depth, int n, int h, int w, int c,

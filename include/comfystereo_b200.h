@@ -189,7 +189,11 @@ CS_API int cs_compose(const uint8_t *left_u8, const uint8_t *right_u8, int n, in
 /* Replaces the body of StereoImageNode.generate (GS:117-269) for n frames that are already
  * resident on the device: prep, blur, per-eye warp + fill, composition, depth outputs, mask.
  * All pointers are device pointers owned by the caller.  workspace >= cs_workspace_bytes(p,
- * chunk, h, w) for some chunk >= 1; the call picks the largest chunk that fits. */
+ * chunk, h, w) for some chunk >= 1; the call picks the largest chunk that fits.
+ * Asynchronous on `stream`.  Small jobs (n*h*w <= two 1080p frames) that repeat with the SAME pointers, sizes and
+ * parameters -- a streaming caller reusing its buffers -- are captured into a CUDA graph on the second call and replayed
+ * with one launch afterwards (the graph holds the pointers, not the contents; COMFYSTEREO_GRAPHS=0 disables it,
+ * cs_host_release drops the cached graphs). */
 CS_API int cs_stereo_batch(const cs_params *p, const float *image, const float *depth, int n, int h,
                     int w, int c, float *stereo, float *depth_l, float *depth_r, float *mask,
                     void *workspace, size_t workspace_bytes, void *stream);

@@ -350,3 +350,43 @@ def test_row_capacity_limits(oracle, fill, wmax):
     dep2 = np.zeros((1, h, wmax + 8, 1), np.float32)
     with pytest.raises(CsError, match="exceeds"):
         node.generate(torch.from_numpy(img2), torch.from_numpy(dep2), **kw)
+
+
+@pytest.mark.parametrize("fill,blur", [("naive", False), ("polylines_sharp", True), ("hybrid_edge", True), ("gpu_warp", True),
+                                       ("gpu_warp_mesh", False)])
+def test_graph_replay_of_repeated_small_calls(oracle, fill, blur):
+    """The second identical small cs_stereo_batch call (same buffers, same parameters) is captured into a CUDA graph and
+    later ones replay it: same results as the direct launches, fresh input data is picked up (the graph holds pointers,
+    not contents), the launch counter advances by the same amount per call, and a changed parameter is a different graph."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from comfystereo_b200 import engine, _lib
+    lib = _lib.lib()
+    h, w = 120, 256
+    imgs = [torch.from_numpy(syn.make_image(1, h, w, seed=s)).cuda() for s in (1, 2)]
+    deps = [torch.from_numpy(syn.make_depth(1, h, w, "scene", seed=s)).cuda() for s in (1, 2)]
+    group = 1 if fill.startswith("gpu_warp") else 0
+    p = engine.make_params(fill, "left-right", 4.0, 0.5, 0.0, 0.5, 2.0, blur, 9.0, 20.0, 2.0, 2, group_size=group)
+    want = []
+    for k in range(2):      # fresh tensors every time: different pointers, so these are direct launches
+        want.append([o.clone() for o in engine.stereo_batch_device(imgs[k].clone(), deps[k].clone(), p)])
+    img, dep = imgs[0].clone(), deps[0].clone()
+    out = engine.stereo_batch_device(img, dep, p)
+    counts = []
+    for rep in range(5):
+        k = rep % 2
+        img.copy_(imgs[k]); dep.copy_(deps[k])
+        lib.cs_launch_count(1)
+        engine.stereo_batch_device(img, dep, p, out=out)
+        counts.append(lib.cs_launch_count(1))
+        torch.cuda.synchronize()
+        for a, b in zip(out, want[k]):
+            assert torch.equal(a, b), (fill, rep)
+    assert len(set(counts)) == 1 and counts[0] > 0, counts
+    p2 = engine.make_params(fill, "left-right", 5.0, 0.5, 0.0, 0.5, 2.0, blur, 9.0, 20.0, 2.0, 2, group_size=group)
+    for _ in range(3):
+        engine.stereo_batch_device(img, dep, p2, out=out)
+    torch.cuda.synchronize()
+    ref = engine.stereo_batch_device(img.clone(), dep.clone(), p2)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
