@@ -465,6 +465,25 @@ def main():
             e2e["large_batch"] = {"value": big / dtl, "unit": "frames/s", "frames": big,
                                   "note": "pageable inputs, 11 GB of results (beyond the 4 GiB page-lock limit of the python host)"}
             del bi, bd
+            # one process, every visible device: the node's own frame sharding (COMFYSTEREO_MULTI_GPU), which a
+            # one-rank-per-GPU launch never exercises
+            ndev = torch.cuda.device_count()
+            if ndev > 1:
+                frames = 16 * ndev
+                mi, md = make_frames(frames, h, w, seed=0)
+                mi, md = torch.from_numpy(mi).pin_memory(), torch.from_numpy(md).pin_memory()
+                mp = p
+                one = engine.stereo_batch_host(mi[:16], md[:16], mp, device=0)
+                for _ in range(2):
+                    many = engine.stereo_batch_multi_gpu(mi, md, mp, list(range(ndev)))
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    many = engine.stereo_batch_multi_gpu(mi, md, mp, list(range(ndev)))
+                dtm = time.perf_counter() - t0
+                same = all(torch.equal(a[:16], b) for a, b in zip(many, one)) if group == 0 else None
+                e2e["one_process_multi_gpu"] = {"value": frames * args.e2e_steps / dtm, "unit": "frames/s", "devices": ndev,
+                                                "frames": frames, "first_shard_equals_single_gpu": same}
+                del mi, md, many, one
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
