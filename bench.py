@@ -184,7 +184,9 @@ def node_params(args):
 
 
 def workload_config(args, frames):
-    return {"workload": f"{args.width}x{args.height} {args.fill}, depth_map_blur on (strength 20, threshold 20, "
+    fill = args.fill + (" [mesh warp]" if os.environ.get("COMFYSTEREO_GPU_WARP", "").lower() == "mesh" and
+                        args.fill == "GPU Warp (Fast)" else "")
+    return {"workload": f"{args.width}x{args.height} {fill}, depth_map_blur on (strength 20, threshold 20, "
                         f"falloff 2.0, vert 6), convergence {args.convergence}, divergence {args.divergence}, "
                         f"stereo_balance {args.balance}, separation {args.separation}, exponent 2, {args.mode} "
                         f"(BASELINE.json configs[1] as a batch)",
@@ -206,7 +208,7 @@ def main():
     import ctypes
     import torch
     import torch.distributed as dist
-    from comfystereo_b200 import StereoImageNode, _lib, engine
+    from comfystereo_b200 import StereoImageNode, _lib, engine, stereoimage_generation
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,7 +222,10 @@ def main():
 
     n, h, w = args.frames, args.height, args.width
     key = engine.FILL_NAME_TO_KEY.get(args.fill, "gpu_warp")
-    group = min(NODE_PARAMS["batch_size"], n) if key == "gpu_warp" else 0
+    if key == "gpu_warp" and stereoimage_generation.MODERNGL_AVAILABLE:     # COMFYSTEREO_GPU_WARP=mesh, as the node decides
+        key = "gpu_warp_mesh"
+    gpu_warp = key in engine.GPU_WARP_KEYS
+    group = min(NODE_PARAMS["batch_size"], n) if gpu_warp else 0
     p = engine.make_params(key, args.mode, args.divergence, args.separation, args.balance, args.convergence, 2.0, True,
                            20.0, 20.0, 2.0, 6, group_size=group)
     # Frame-wise sharding: the global batch of n * world frames is cut into contiguous ranges with
@@ -332,7 +337,7 @@ def main():
     kernels = {lib.cs_profile_kernel_name(i).decode(): (k_ms[i], k_n[i]) for i in range(nk) if k_n[i] > 0}
     peak, peak_src = peaks()
     px_step = n * h * w
-    cls = "gw_sbs" if key == "gpu_warp" else "cpu_sbs"
+    cls = "gw_sbs" if gpu_warp else "cpu_sbs"
     if args.mode.endswith("anaglyph") or args.mode in ("left-only", "only-right"):
         cls = "anaglyph"
     path_bytes = BYTES_PER_PX[cls] * px_step
@@ -439,7 +444,7 @@ def main():
             # the result tensors hold d2h_bytes_per_step; of those, the depth outputs (3 identical channels) and the
             # mask (0/1) crossed PCIe as one channel / one byte per pixel and were expanded by host threads
             # (depth: the byte k of k/255 for the CPU techniques, one float for GPU Warp; mask: one byte)
-            dbytes = 4 if key == 'gpu_warp' else 1
+            dbytes = 4 if gpu_warp else 1
             bus = int(np.prod(s_shape)) * 4 + 2 * int(np.prod(d_shape)) // 3 * dbytes + int(np.prod(m_shape))
             e2e["d2h_bus_bytes_per_step"] = bus
             e2e["transport"] = "compact depth/mask"

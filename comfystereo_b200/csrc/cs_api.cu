@@ -16,6 +16,18 @@ namespace cs {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int sm_count() {
+    static std::atomic<int> cached[64];      // per device ordinal; 0 = not asked yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 // ---- per-kernel timing -------------------------------------------------------------------
 struct ProfRec { int id; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;

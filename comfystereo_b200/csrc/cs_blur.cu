@@ -652,7 +652,7 @@ cudaError_t launch_blur(const float* gray, FrameStats* stats, int scale_mode, in
     const int tiles_y = (h + kTileY - 1) / kTileY;
     const int items = segs * tiles_y;
     // few CTAs per frame so the 4 min/max atomics per CTA stay cheap; >= 4 waves in total
-    int per_frame = (148 * 5 * 4 + n - 1) / n;
+    int per_frame = (sm_count() * 5 * 4 + n - 1) / n;
     if (per_frame > items) per_frame = items;
     if (per_frame < 1) per_frame = 1;
     const int rw = (kSeg + bs + kRowPad + 3) & ~3;

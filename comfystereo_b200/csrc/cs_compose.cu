@@ -92,7 +92,7 @@ cudaError_t launch_compose(const uint32_t* left, const uint32_t* right, int n, i
                     ((uintptr_t)stereo % 16 == 0) && ((uintptr_t)mask % 16 == 0);
     int64_t nitem = npx_out / (vec ? 4 : 1);
     int bx = (int)((nitem + 255) / 256);
-    const int cap = 148 * 8 * 2;
+    const int cap = sm_count() * 8 * 2;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     prof_begin(K_COMPOSE, s);
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256) k_compact_outputs(const float* __restrict
 cudaError_t launch_compact_outputs(const float* dl3, const float* dr3, const float* mask, int64_t npx, int64_t nmask,
                                    int depth_u8, void* cdl, void* cdr, uint8_t* cmask, cudaStream_t s) {
     prof_begin(K_MISC, s);
-    if (depth_u8) k_compact_outputs<true><<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
-    else k_compact_outputs<false><<<148 * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
+    if (depth_u8) k_compact_outputs<true><<<sm_count() * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
+    else k_compact_outputs<false><<<sm_count() * 8, 256, 0, s>>>(dl3, dr3, mask, npx, nmask, cdl, cdr, cmask);
     prof_end(K_MISC, s);
     count_launch();
     return cudaGetLastError();

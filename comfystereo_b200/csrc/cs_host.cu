@@ -56,8 +56,9 @@ struct HostCtx {
     bool ready = false;
 };
 
-static std::mutex g_mu[16];   // one pipeline per device; devices run concurrently
-static HostCtx g_ctx[16];
+constexpr int kMaxDevices = 64;          // device ordinals this process can address (CUDA's own limit per process)
+static std::mutex g_mu[kMaxDevices];     // one pipeline per device; devices run concurrently
+static HostCtx g_ctx[kMaxDevices];
 
 static void ctx_free(HostCtx& c) {
     if (!c.ready) return;
@@ -308,7 +309,7 @@ double cs_host_stream_bandwidth(size_t bytes, int threads) {
 }
 
 void cs_host_release(void) {
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < kMaxDevices; ++i) {
         std::lock_guard<std::mutex> lk(g_mu[i]);
         ctx_free(g_ctx[i]);
     }
@@ -327,7 +328,7 @@ int cs_stereo_batch_host_progress(const cs_params* p, const float* image, const 
 #define HOST_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cs::fail(CS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
     if (!p || !image || !depth || !stereo || !depth_l || !depth_r || !mask) HOST_FAIL(CS_ERR_ARG, "cs_stereo_batch_host: NULL pointer");
     if (n < 1 || h < 1 || w < 2 || c < 1) HOST_FAIL(CS_ERR_ARG, "cs_stereo_batch_host: bad size");
-    if (device < 0 || device >= 16) HOST_FAIL(CS_ERR_ARG, "cs_stereo_batch_host: bad device %d", device);
+    if (device < 0 || device >= cs::kMaxDevices) HOST_FAIL(CS_ERR_ARG, "cs_stereo_batch_host: bad device %d", device);
     int ho, wo, hm, wm;
     int rc = cs_output_dims(p, h, w, &ho, &wo, &hm, &wm);
     if (rc) return rc;

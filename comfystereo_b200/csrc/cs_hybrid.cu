@@ -197,7 +197,7 @@ cudaError_t launch_hybrid(const WarpArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     int64_t npx = (int64_t)a.h * a.w;
     int bx = (int)((npx + 255) / 256);
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > sm_count() * 8) bx = sm_count() * 8;
     prof_begin(K_HYBRID_GAPFILL, s);
     k_hybrid_gapfill<<<dim3(bx, a.n, 2), 256, 0, s>>>(a, exp(-0.5), exp(-1.0));
     prof_end(K_HYBRID_GAPFILL, s);
@@ -234,7 +234,7 @@ cudaError_t launch_hybrid_plus(const WarpArgs& a, cudaStream_t s) {
     if ((e = launch_polylines(p, s)) != cudaSuccess) return e;
     const int64_t total = (int64_t)a.n * a.h * a.w;
     int bx = (int)((total + 255) / 256);
-    if (bx > 148 * 16) bx = 148 * 16;
+    if (bx > sm_count() * 16) bx = sm_count() * 16;
     for (int eye = 0; eye < 2; ++eye) {
         if (a.eye[eye].passthrough || !a.out[eye]) continue;
         prof_begin(K_MISC, s);

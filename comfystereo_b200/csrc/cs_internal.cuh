@@ -186,6 +186,7 @@ __device__ __forceinline__ int64_t fused_index(const WarpArgs& a, int eye, int f
 }
 
 void count_launch();
+int sm_count();           // SMs of the current device (148 on a B200), for grid sizing
 void release_graphs();   // cs_api.cu: drops the cached CUDA graphs of small repeated cs_stereo_batch calls
 // Optional per-kernel timing (bench.py): CUDA events recorded on the launch stream around every kernel.
 enum KernelId { K_PREPARE = 0, K_EDGE_DIST, K_BLUR_BLEND, K_DEPTH_OUT, K_WARP_ROWS, K_POLY_FAST, K_POLY_EXACT,

@@ -191,8 +191,8 @@ cudaError_t launch_prepare(const float* image, const float* depth, int n, int h,
     const int64_t npx = (int64_t)h * w;
     int64_t nquad = npx >> 2;
     int bx = (int)((nquad + 255) / 256);
-    // a few waves of 148 SMs x 8 resident CTAs; grid-stride the rest
-    const int cap = 148 * 8 * 2;
+    // a few waves of SMs x 8 resident CTAs; grid-stride the rest
+    const int cap = sm_count() * 8 * 2;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid(bx, n);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_minmax(const float* __restrict__ src, i
 
 cudaError_t launch_minmax(const float* src, int n, int64_t npx, FrameStats* stats, cudaStream_t s) {
     int bx = (int)((npx + 1023) / 1024);
-    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx > sm_count() * 4) bx = sm_count() * 4;
     if (bx < 1) bx = 1;
     prof_begin(K_MISC, s);
     k_minmax<<<dim3(bx, n), 256, 0, s>>>(src, npx, stats);
@@ -270,7 +270,7 @@ cudaError_t launch_export_stats(const FrameStats* stats, int n, int which, float
 // ---------------------------------------------------------------- depth outputs
 // out_kind 1 (CPU techniques, quirk Q1): u8 = trunc(d255 * 255) mod 256, value = u8 / 255
 //          2 (GPU Warp, SIG:1125 + GS:165): d255 / 255 if the sub-batch max > 1, clamp to [0,1]
-// Every output pixel is three identical floats; a thread writes one float4 = floats 4m..4m+3.
+// Every output pixel is three identical floats; a thread takes 4 pixels = three float4 per output.
 __device__ __forceinline__ float depth_out_value(float d255, int out_kind, bool div255) {
     if (out_kind == 1) {
         float v = d255 * 255.0f;
@@ -315,20 +315,21 @@ __global__ void __launch_bounds__(256) k_depth_out(const float* __restrict__ src
     const float* sr = src_r + (int64_t)frame * npx;
     float4* ol = reinterpret_cast<float4*>(out_l + (int64_t)frame * npx * 3);
     float4* orr = reinterpret_cast<float4*>(out_r + (int64_t)frame * npx * 3);
-    const int64_t nvec = vec_ok ? ((npx * 3) >> 2) : 0;
-    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nvec;
-         m += (int64_t)gridDim.x * blockDim.x) {
-        int64_t p0 = (4 * m) / 3, p1 = (4 * m + 3) / 3;
-        float a0 = depth_out_value(sl[p0] * scale, out_kind, div_l);
-        float a1 = depth_out_value(sl[p1] * scale, out_kind, div_l);
-        float b0 = depth_out_value(sr[p0] * scale, out_kind, div_r);
-        float b1 = depth_out_value(sr[p1] * scale, out_kind, div_r);
-        // floats 4m..4m+3 belong to pixel p0 until the first multiple of 3 past 4m
-        int k = (int)(3 * (p0 + 1) - 4 * m);  // how many of the four floats are p0's (1..3)
-        float4 va = make_float4(a0, k > 1 ? a0 : a1, k > 2 ? a0 : a1, a1);
-        float4 vb = make_float4(b0, k > 1 ? b0 : b1, k > 2 ? b0 : b1, b1);
-        st_stream_f4(ol + m, va, pol);
-        st_stream_f4(orr + m, vb, pol);
+    // vector path: 4 pixels per thread, one 128-bit load per source and three 128-bit streaming stores per output
+    const int64_t nquad = vec_ok ? (npx >> 2) : 0;
+    const int64_t nvec = nquad * 3;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 l = reinterpret_cast<const float4*>(sl)[q], r = reinterpret_cast<const float4*>(sr)[q];
+        const float a0 = depth_out_value(l.x * scale, out_kind, div_l), a1 = depth_out_value(l.y * scale, out_kind, div_l);
+        const float a2 = depth_out_value(l.z * scale, out_kind, div_l), a3 = depth_out_value(l.w * scale, out_kind, div_l);
+        const float b0 = depth_out_value(r.x * scale, out_kind, div_r), b1 = depth_out_value(r.y * scale, out_kind, div_r);
+        const float b2 = depth_out_value(r.z * scale, out_kind, div_r), b3 = depth_out_value(r.w * scale, out_kind, div_r);
+        st_stream_f4(ol + 3 * q, make_float4(a0, a0, a0, a1), pol);
+        st_stream_f4(ol + 3 * q + 1, make_float4(a1, a1, a2, a2), pol);
+        st_stream_f4(ol + 3 * q + 2, make_float4(a2, a3, a3, a3), pol);
+        st_stream_f4(orr + 3 * q, make_float4(b0, b0, b0, b1), pol);
+        st_stream_f4(orr + 3 * q + 1, make_float4(b1, b1, b2, b2), pol);
+        st_stream_f4(orr + 3 * q + 2, make_float4(b2, b3, b3, b3), pol);
     }
     {   // scalar path for frames that are not vectorisable
         for (int64_t f = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < npx * 3;
@@ -344,12 +345,13 @@ cudaError_t launch_depth_out(const float* src_l, const float* src_r, const Frame
                              int h, int w, int src_kind, int out_kind, int group, float* out_l,
                              float* out_r, cudaStream_t s) {
     const int64_t npx = (int64_t)h * w;
-    int64_t nvec = (npx * 3) >> 2;
-    int bx = (int)((nvec + 255) / 256);
-    const int cap = 148 * 8 * 2;
+    int64_t nquad = (npx + 3) >> 2;
+    int bx = (int)((nquad + 255) / 256);
+    const int cap = sm_count() * 8 * 2;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    const int vec = (npx % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0);
+    const int vec = (npx % 4 == 0) && ((uintptr_t)out_l % 16 == 0) && ((uintptr_t)out_r % 16 == 0) &&
+                    ((uintptr_t)src_l % 16 == 0) && ((uintptr_t)src_r % 16 == 0);
     prof_begin(K_DEPTH_OUT, s);
     k_depth_out<<<dim3(bx, n), 256, 0, s>>>(src_l, src_r, stats, n, npx, src_kind, out_kind,
                                             group < 1 ? 1 : group, vec, out_l, out_r);
@@ -367,7 +369,7 @@ __global__ void k_quantize(const float* __restrict__ image, int64_t total_px, ui
 
 cudaError_t launch_quantize(const float* image, int64_t total_px, uint32_t* out, cudaStream_t s) {
     int bx = (int)((total_px + 255) / 256);
-    if (bx > 148 * 16) bx = 148 * 16;
+    if (bx > sm_count() * 16) bx = sm_count() * 16;
     if (bx < 1) bx = 1;
     prof_begin(K_MISC, s);
     k_quantize<<<bx, 256, 0, s>>>(image, total_px, out);
@@ -400,7 +402,7 @@ cudaError_t launch_shift_indices(const float* nd, int n, int h, int w, double di
                                  double expo, int kind, int32_t* out, cudaStream_t s) {
     int64_t total = (int64_t)n * h * w;
     int bx = (int)((total + 255) / 256);
-    if (bx > 148 * 16) bx = 148 * 16;
+    if (bx > sm_count() * 16) bx = sm_count() * 16;
     if (bx < 1) bx = 1;
     prof_begin(K_MISC, s);
     k_shift_indices<<<bx, 256, 0, s>>>(nd, total, w, div_px, sep_px, expo, kind, out);

@@ -36,7 +36,7 @@ def main():
     base = min(n, 4)
     img = np.tile(syn.make_image(base, h, w, seed=0), (-(-n // base), 1, 1, 1))[:n]
     dep = np.tile(syn.make_depth(base, h, w, a.kind, seed=0), (-(-n // base), 1, 1, 1))[:n]
-    group = min(12, n) if a.fill == "gpu_warp" else 0
+    group = min(12, n) if a.fill.startswith("gpu_warp") else 0
     p = engine.make_params(a.fill, a.mode, a.divergence, a.separation, a.balance, 0.5, 2.0, not a.no_blur, 20.0, 20.0, 2.0, 6,
                            group_size=group)
     img_d, dep_d = torch.from_numpy(img).to(dev), torch.from_numpy(dep).to(dev)

@@ -21,6 +21,7 @@ cap naive_interp_noblur 4 --fill naive_interpolating --no-blur
 cap inverse_anaglyph 6 --fill inverse --mode red-cyan-anaglyph
 cap hybrid 7 --fill hybrid_edge
 cap gpuwarp 6 --fill gpu_warp
+cap meshwarp 7 --fill gpu_warp_mesh
 cap gpuwarp4k 6 --fill gpu_warp --width 3840 --height 2160 --mode red-cyan-anaglyph --divergence 10
 cap poly8k 6 --fill polylines_sharp --width 7680 --height 3840 --frames 2 --balance 0.5
 python tools/ncu_table.py /dev/null 2>/dev/null | head -2 > gpurun_out/r02_ncu_kernels.md

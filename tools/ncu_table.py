@@ -16,6 +16,7 @@ def num(v, unit):
     elif u in ("ns", "nsecond"): v *= 1e-3
     elif u in ("s", "second"): v *= 1e6
     return v
+# DRAM % of peak = achieved GB/s / MEASURED_PEAKS.json hbm_gbs (6548.5); ncu's own dram__throughput metric is not in --set full here
 print("| capture | kernel | grid x block | regs | time us | DRAM rd+wr MB | achieved GB/s | DRAM % of peak | L2 hit % | issue % | occupancy % | lanes/32 | Mwarp-inst |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for rep in sys.argv[1:]:
@@ -34,4 +35,4 @@ for rep in sys.argv[1:]:
         gbs = (d.get("rd", 0) + d.get("wr", 0)) / max(d.get("us", 1), 1e-9) / 1e3
         cap = os.path.basename(rep).replace("r02_ncu_", "").replace(".ncu-rep", "")
         print(f"| {cap} | `{name}` | {int(d.get('grid', 0))} x {int(d.get('block', 0))} | {int(d.get('regs', 0))} | {d.get('us', 0):.1f} | {mb:.1f} | {gbs:.0f} | "
-              f"{d.get('dram%', 0):.1f} | {d.get('l2hit%', 0):.1f} | {d.get('issue%', 0):.1f} | {d.get('occ%', 0):.1f} | {d.get('lanes', 0):.1f} | {d.get('inst', 0) / 1e6:.1f} |")
+              f"{100 * gbs / 6548.5:.1f} | {d.get('l2hit%', 0):.1f} | {d.get('issue%', 0):.1f} | {d.get('occ%', 0):.1f} | {d.get('lanes', 0):.1f} | {d.get('inst', 0) / 1e6:.1f} |")
