@@ -228,11 +228,12 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
         a.conv = (float)p->convergence_point;
         a.scratch = ws.warp_scratch; a.scratch_bytes = ws.warp_scratch_bytes;
         a.flags = flags;
-        // Polylines and the row techniques write the composed tensors themselves in the side-by-side / top-bottom modes
-        // (when both eyes are warped)
+        // Polylines, the row techniques and Hybrid Edge (its gap-fill pass) write the composed tensors themselves in the
+        // side-by-side / top-bottom modes (when both eyes are warped)
         const bool rows = p->fill == CS_FILL_NONE || p->fill == CS_FILL_NAIVE || p->fill == CS_FILL_NAIVE_INTERP ||
                           p->fill == CS_FILL_INVERSE || p->fill == CS_FILL_NONE_POST || p->fill == CS_FILL_INVERSE_POST;
-        const bool fused = (rows || p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP) &&
+        const bool fused = (rows || p->fill == CS_FILL_POLYLINES_SOFT || p->fill == CS_FILL_POLYLINES_SHARP ||
+                            (p->fill == CS_FILL_HYBRID_EDGE && w % 4 == 0)) &&
                            p->mode >= CS_MODE_LEFT_RIGHT && p->mode <= CS_MODE_BOTTOM_TOP &&
                            !eye[0].passthrough && !eye[1].passthrough && !(flags & 16);
         if (fused) { a.fused_stereo = stereo; a.fused_mask = mask; a.fused_mode = p->mode; }

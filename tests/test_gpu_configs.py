@@ -220,6 +220,29 @@ def test_row_techniques_compose_in_the_fill_kernel(node, oracle, fill):
                 assert np.array_equal(a_, b_)
 
 
+def test_hybrid_edge_composes_in_the_gapfill_kernel(node, oracle):
+    """Hybrid Edge writes the composed tensor and the mask from its gap-fill pass when the width is a multiple of 4: same
+    bytes as gap fill in place + k_compose (test flag 16; width 333 never fuses), oracle within 1 LSB (exp: DESIGN.md 7)."""
+    from comfystereo_b200 import _lib
+    lib = _lib.lib()
+    for w in (352, 333):
+        img = syn.make_image(2, 80, w, seed=19, black_box=True)
+        dep = syn.make_depth(2, 80, w, "scene", seed=19)
+        for mode in ("left-right", "right-left", "top-bottom", "bottom-top"):
+            got, p = run(node, img, dep, fill_technique="Imperfect fill - Hybrid Edge", modes=mode, divergence=7.0, separation=-0.3)
+            want = oracle.node_generate(img, dep, **p)
+            assert np.abs(q8(got[0]).astype(np.int32) - q8(want[0]).astype(np.int32)).max() <= 1
+            assert np.array_equal(q8(got[1]), q8(want[1])) and np.array_equal(q8(got[2]), q8(want[2]))
+            assert (got[3] != want[3]).mean() <= 1e-3 and got[3].sum() > 0
+            lib.cs_set_test_flags(16)
+            try:
+                alt, _ = run(node, img, dep, fill_technique="Imperfect fill - Hybrid Edge", modes=mode, divergence=7.0, separation=-0.3)
+            finally:
+                lib.cs_set_test_flags(0)
+            for a_, b_ in zip(got, alt):
+                assert np.array_equal(a_, b_)
+
+
 def test_progress_is_reported_per_chunk_and_depth_batch_may_be_longer(node, oracle, monkeypatch):
     """GS:173 / GS:262: the reference moves its progress bar per sub-batch / per frame; the node reports every chunk of
     frames as its results land (in order, on the calling thread) and the updates add up to the batch size.  A depth
