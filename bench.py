@@ -356,6 +356,8 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             traffic_px = json.load(f)["dram_bytes_per_input_pixel"]   # dram read+write per input pixel, from an ncu capture
+        if key == "gpu_warp_mesh" and "k_gpuwarp_mesh" in traffic_px:     # the mesh kernels are timed under k_gpuwarp's id
+            traffic_px["k_gpuwarp"] = traffic_px["k_gpuwarp_mesh"]
     except Exception:  # noqa: BLE001
         pass
     roofline = None

@@ -19,7 +19,7 @@ cap polylines_soft 6 --fill polylines_soft
 cap naive 5 --fill naive
 cap naive_interp_noblur 4 --fill naive_interpolating --no-blur
 cap inverse_anaglyph 6 --fill inverse --mode red-cyan-anaglyph
-cap hybrid 7 --fill hybrid_edge
+cap hybrid 6 --fill hybrid_edge
 cap gpuwarp 6 --fill gpu_warp
 cap meshwarp 7 --fill gpu_warp_mesh
 cap gpuwarp4k 6 --fill gpu_warp --width 3840 --height 2160 --mode red-cyan-anaglyph --divergence 10
