@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) k_mesh_keep(const GpuWarpArgs a) {
 }
 
 // One CTA per (output row, frame), both eyes in turn, composed into the final stereo layout like k_gpuwarp.
-__global__ void __launch_bounds__(256) k_meshwarp(const GpuWarpArgs a) {
+__global__ void __launch_bounds__(512) k_meshwarp(const GpuWarpArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
     const int nwords = (w + 31) >> 5;
@@ -565,8 +565,10 @@ cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)a.w * 24 + (size_t)nwords * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_meshwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // a wide row's shared memory (24 B per column) leaves room for two CTAs per SM: make them 512 threads, like k_gpuwarp
+    const int tpb = smem > 56 * 1024 ? 512 : 256;
     prof_begin(K_GPUWARP, s);
-    k_meshwarp<<<dim3(a.h, a.n), 256, smem, s>>>(a);
+    k_meshwarp<<<dim3(a.h, a.n), tpb, smem, s>>>(a);
     prof_end(K_GPUWARP, s);
     count_launch();
     return cudaGetLastError();

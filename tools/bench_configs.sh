@@ -1,7 +1,7 @@
 #!/bin/bash
 # Device-resident throughput of the five BASELINE.json configs (+ the other techniques at 1080p) -> gpurun_out/configs.jsonl
 out=gpurun_out/configs.jsonl; : > $out
-run() { timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --strong-frames 0 "$@" 2>/dev/null | tail -1 >> $out; }
+run() { timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --strong-frames 0 "$@" 2>/dev/null | tail -1 >> $out; }
 run --height 512 --width 512 --frames 64 --fill "Fill - Naive"
 run --fill "Fill - Polylines Sharp"
 run --fill "Imperfect fill - Hybrid Edge"
