@@ -60,7 +60,9 @@ def parse_args():
     ap.add_argument("--no-extra-e2e", action="store_true", help="skip the pageable-input / large-output e2e legs")
     ap.add_argument("--chunk", type=int, default=0, help="frames per kernel sequence (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=0,
+                    help="frames of the CPU baseline sample (0 = 32 for the cpu_baseline leg, about 7 s of host work on 16 cores; "
+                         "4 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -155,7 +157,7 @@ def run_reference(args):
         return
     import oracle as orc
     cores = orc.set_threads(len(os.sched_getaffinity(0)))   # the threads the OpenMP loops really get
-    sample = args.cpu_frames
+    sample = args.cpu_frames or 4
     times = []
     for i in range(args.warmup + args.steps):
         fps, dt = cpu_baseline(args, sample)
@@ -494,10 +496,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, dt = cpu_baseline(args, args.cpu_frames)
+        cpu_frames = args.cpu_frames or 32
+        val, dt = cpu_baseline(args, cpu_frames)
         import oracle as orc
         cpu = {"value": val, "unit": "frames/s", "cores": orc.set_threads(0), "kind": "port",
-               "sample": f"{args.cpu_frames} frame(s) of the same workload, oracle/stereo_oracle.c with OpenMP over rows, "
+               "sample": f"{cpu_frames} frame(s) of the same workload, oracle/stereo_oracle.c with OpenMP over rows, "
                          f"{dt:.2f} s"}
 
     if rank == 0:

@@ -599,7 +599,10 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
     // Small jobs (a frame or two) are bound by launch latency, not by the kernels: the second identical call -- same
     // buffers, same parameters, what a streaming caller that reuses its tensors makes -- is captured into a CUDA graph
     // and every later one replays it with a single launch.
-    if (graphs_enabled() && (size_t)n * h * w <= kGraphMaxPixels && !g_prof_on.load(std::memory_order_relaxed)) {
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;     // a caller building its own graph gets plain launches
+    if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) { (void)cudaGetLastError(); capturing = cudaStreamCaptureStatusActive; }
+    if (graphs_enabled() && (size_t)n * h * w <= kGraphMaxPixels && !g_prof_on.load(std::memory_order_relaxed) &&
+        capturing == cudaStreamCaptureStatusNone) {
         GraphKey key;
         memset(&key, 0, sizeof(key));
         key.params = *p;
