@@ -413,3 +413,41 @@ def test_graph_replay_of_repeated_small_calls(oracle, fill, blur):
     ref = engine.stereo_batch_device(img.clone(), dep.clone(), p2)
     for a, b in zip(out, ref):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("fill,blur", [("polylines_sharp", True), ("naive", False), ("gpu_warp", True)])
+def test_hot_path_is_capturable_in_a_callers_cuda_graph(fill, blur):
+    """A caller may record cs_stereo_batch into its own CUDA graph (torch.cuda.graph): every launch of the chunk sequence is
+    stream-ordered with no host synchronisation, and the library's own graph cache steps aside while the stream captures."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from comfystereo_b200 import engine
+    h, w = 96, 200
+    img = torch.from_numpy(syn.make_image(2, h, w, seed=5)).cuda()
+    dep = torch.from_numpy(syn.make_depth(2, h, w, "scene", seed=5)).cuda()
+    p = engine.make_params(fill, "left-right", 5.0, 0.3, 0.0, 0.5, 2.0, blur, 9.0, 20.0, 2.0, 2,
+                           group_size=2 if fill == "gpu_warp" else 0)
+    want = [o.clone() for o in engine.stereo_batch_device(img, dep, p)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):                      # includes the calls that would build the library's own graph
+            engine.stereo_batch_device(img, dep, p)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = engine.stereo_batch_device(img, dep, p)
+    for o in outs:
+        o.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want):
+        assert torch.equal(a, b)
+    img2 = torch.from_numpy(syn.make_image(2, h, w, seed=6)).cuda()
+    want2 = [o.clone() for o in engine.stereo_batch_device(img2, dep, p)]
+    img.copy_(img2)
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want2):
+        assert torch.equal(a, b)
