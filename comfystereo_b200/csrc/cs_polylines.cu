@@ -25,6 +25,8 @@
 #include <cstdlib>
 
 #include "cs_internal.cuh"
+
+#include <atomic>
 #include "cs_poly_core.cuh"
 
 namespace cs {
@@ -821,11 +823,16 @@ static bool plan_for(int nw, const WarpArgs& a, bool sharp, bool force_tiles, Po
 template <int NW, bool SHARP, int TPS>
 static cudaError_t launch_tiles_occ(const WarpArgs& a, const PolyPlan& p, int* counters, int* flags, int* list, cudaStream_t s) {
     using L = PolyLayout<NW, SHARP>;
-    static bool attr_done = false;   // benign race: the attribute is idempotent
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_polylines<NW, SHARP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes);
+    // the opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of the function: once per device
+    // (benign race: setting it twice is harmless)
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !((attr_done.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(k_polylines<NW, SHARP, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_relaxed);
     }
     prof_begin(K_POLY_FAST, s);
     k_polylines<NW, SHARP, TPS><<<dim3(p.max_tiles, a.h, 2 * a.n), NW * 32, L::kBytes, s>>>(a, p.g, flags, list, counters, a.flags);

@@ -286,6 +286,18 @@ def test_one_process_multi_gpu_sharding(node, oracle, monkeypatch):
         one = [o.numpy() for o in engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), prm, device=0)]
         for a, b in zip(got, one):
             assert np.array_equal(a, b)
+    # full-width rows: the Polylines CTAs need the > 48 KB shared-memory opt-in, a per-DEVICE function attribute (a bug once:
+    # it was set for the first device only)
+    img = syn.make_image(n, 24, 1920, seed=72)
+    dep = syn.make_depth(n, 24, 1920, "scene", seed=72)
+    for fill in ("Fill - Polylines Sharp", "Fill - Polylines Soft", "Fill - Naive", "Imperfect fill - Hybrid Edge", "GPU Warp (Fast)"):
+        got, p = run(node, img, dep, fill_technique=fill, batch_size=3, divergence=4.0)
+        key = engine.FILL_NAME_TO_KEY[fill]
+        prm = engine.make_params(key, "left-right", 4.0, 0.0, 0.0, 0.5, 2.0, True, 20.0, 20.0, 2.0, 6,
+                                 group_size=3 if key == "gpu_warp" else 0)
+        one = [o.numpy() for o in engine.stereo_batch_host(torch.from_numpy(img), torch.from_numpy(dep), prm, device=0)]
+        for a, b in zip(got, one):
+            assert np.array_equal(a, b), fill
 
 
 def test_4k_polylines_sharp_natural_tiles(node, oracle):
