@@ -43,7 +43,8 @@ struct Tab {
     const uint16_t* WSP;     // [npts]   interval (k, k+1): source index of the segment that wins at every centre strictly
                              //          inside, or kUnresolved | own index when that is not known (none, several, ties)
     const float* Q;          // [w + 2]  closeness, padded: Q[pt_slot(i)] belongs to source point i (both sentinels 0)
-    const uint32_t* IMGP;    // [w + 2]  RGBX of the window's source columns, padded the same way (edge pixels repeated)
+    const uint32_t* IMGP;    // [npts]   RGBX of source point i's pixel (both sentinels repeat the edge pixels): same index as X,
+                             //          so the sweep reaches x and colour of a segment's two ends from one address
     const uint16_t* START;   // [tw + 3] first sorted rank of bucket b = floor(x) - t0 + 1 (0 = left of t0, tw + 1 = right)
     int w, npts, nsg;        // source window width, points, segments
     int t0;                  // absolute output column of bucket 1
@@ -234,7 +235,7 @@ CS_HDN uint32_t exact_column(const Tab& c, int col) {
             if (sp < 0) { pa = pb; continue; }
         }
         const int cl = slot_col(pt_slot<SHARP>(sp), c.w), cr = slot_col(pt_slot<SHARP>(sp + 1), c.w);
-        const uint32_t pl = c.IMGP[cl + 1];
+        const uint32_t pl = c.IMGP[sp];
         double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
         if (cl != cr) {
             // ip = (ctr - x0) / (x1 - x0) with the reference's float32 subtraction in the denominator
@@ -242,7 +243,7 @@ CS_HDN uint32_t exact_column(const Tab& c, int col) {
             const double x1 = (double)c.X[sp + 1];
             const double den = round24_even(x1 - x0);
             const double ip = (ctr - x0) / den;
-            const uint32_t pr = c.IMGP[cr + 1];
+            const uint32_t pr = c.IMGP[sp + 1];
             const double om = 1.0 - ip;
             double t0 = v0 * om, t1 = u8_to_f64(pr & 255u) * ip;
             v0 = t0 + t1;
@@ -295,14 +296,14 @@ __device__ __noinline__ uint32_t exact_column_warp(const Tab& c, int col) {
             }
             if (sp >= 0) {
                 const int cl = slot_col(pt_slot<SHARP>(sp), c.w), cr = slot_col(pt_slot<SHARP>(sp + 1), c.w);
-                const uint32_t pl = c.IMGP[cl + 1];
+                const uint32_t pl = c.IMGP[sp];
                 double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
                 if (cl != cr) {
                     const double x0 = (double)c.X[sp];
                     const double x1 = (double)c.X[sp + 1];
                     const double den = round24_even(x1 - x0);
                     const double ip = (ctr - x0) / den;
-                    const uint32_t pr = c.IMGP[cr + 1];
+                    const uint32_t pr = c.IMGP[sp + 1];
                     const double om = 1.0 - ip;
                     double a = v0 * om, b = u8_to_f64(pr & 255u) * ip;
                     v0 = a + b;
@@ -332,6 +333,14 @@ __device__ __noinline__ uint32_t exact_column_warp(const Tab& c, int col) {
 #endif
 
 // ------------------------------------------------------------------ float32 path
+// 2^23 + byte `ch` of p, as a float: one PRMT on the device
+CS_HD float u8f_biased(uint32_t p, int ch) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(p, 0x4B000000u, 0x7440u | (uint32_t)ch));
+#else
+    return 8388608.0f + (float)((p >> (8 * ch)) & 255u);
+#endif
+}
 CS_HD float u8f(uint32_t p, int ch) {
 #ifdef __CUDA_ARCH__
     // 0x4B0000vv is 2^23 + v: one PRMT and one FADD, no I2F
@@ -374,7 +383,8 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
     float pa = c.SX[k0];
     uint32_t bad = 0;
     // (not unrolled: the trip count differs from lane to lane, and an unrolled body plus a remainder loop makes the warp
-    // execute both for the longest lane)
+    // execute both for the longest lane; fetching sub-interval k + 1's tables while k is accumulated -- software
+    // pipelining by hand -- costs registers the 64-register budget does not have: measured 3 % slower)
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
@@ -388,14 +398,16 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
         const float sig = d - 2e-7f;
         const int sp = (int)(inf & (kUnresolved - 1u));
         const float x0 = c.X[sp], x1 = c.X[sp + 1];
-        const uint32_t pl = c.IMGP[pt_slot<SHARP>(sp)], pr = c.IMGP[pt_slot<SHARP>(sp + 1)];
+        const uint32_t pl = c.IMGP[sp], pr = c.IMGP[sp + 1];
         const float den = x1 - x0;                       // the reference's float32 subtraction, bit for bit
         const float num = fmaf(0.5f, d, fromp - x0);     // centre - x0
         const float ip = num * fast_rcp(den);
-        const float l0 = u8f(pl, 0), l1 = u8f(pl, 1), l2 = u8f(pl, 2);
-        const float v0 = fmaf(ip, u8f(pr, 0) - l0, l0);
-        const float v1 = fmaf(ip, u8f(pr, 1) - l1, l1);
-        const float v2 = fmaf(ip, u8f(pr, 2) - l2, l2);
+        // (2^23 + r) - (2^23 + l) is r - l exactly: the right pixel's bias never has to be removed
+        const float L0 = u8f_biased(pl, 0), L1 = u8f_biased(pl, 1), L2 = u8f_biased(pl, 2);
+        const float l0 = L0 - 8388608.0f, l1 = L1 - 8388608.0f, l2 = L2 - 8388608.0f;
+        const float v0 = fmaf(ip, u8f_biased(pr, 0) - L0, l0);
+        const float v1 = fmaf(ip, u8f_biased(pr, 1) - L1, l1);
+        const float v2 = fmaf(ip, u8f_biased(pr, 2) - L2, l2);
         a0 = fmaf(v0, sig, a0);
         a1 = fmaf(v1, sig, a1);
         a2 = fmaf(v2, sig, a2);

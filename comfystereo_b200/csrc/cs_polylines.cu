@@ -302,7 +302,7 @@ struct PolyGeom {             // per eye
 template <int NW, bool SHARP>
 struct PolyLayout {
     static constexpr int NT = NW * 32, NP = NT * 8, CPT = SHARP ? 4 : 8, SCAP = NT * CPT;
-    static constexpr size_t kBytes = 4 * (size_t)(NP + 8) + 4 * (size_t)NP + 4 * (size_t)NP + 2 * 4 * (size_t)(SCAP + 8) +
+    static constexpr size_t kBytes = 4 * (size_t)(NP + 8) + 4 * (size_t)NP + 4 * (size_t)NP + 4 * (size_t)(SCAP + 8) + 4 * (size_t)(NP + 8) +
                                      8 * (size_t)NT + 2 * (size_t)NP + 2 * (size_t)(NP + 16) + 2 * (size_t)NP +
                                      2 * (size_t)(SCAP + 8);
     // source columns a CTA can take: every point incl. both sentinels fits the NP slots (4 columns of slack for the
@@ -342,9 +342,9 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     uint32_t* ER = reinterpret_cast<uint32_t*>(SX + NP);         // [NP]      END | REACH << 16
     float* QA = reinterpret_cast<float*>(ER + NP);               // [SCAP + 8] closeness, padded by one on either side
     float* Q = QA + 3;
-    uint32_t* IMGA = reinterpret_cast<uint32_t*>(QA + SCAP + 8); // [SCAP + 8] RGBX, padded the same way
+    uint32_t* IMGA = reinterpret_cast<uint32_t*>(QA + SCAP + 8); // [NP + 8]  RGBX per source point (laid out like X)
     uint32_t* IMGP = IMGA + 3;
-    float* TMX = reinterpret_cast<float*>(IMGA + SCAP + 8);      // [NT] max of every point up to the end of thread t's
+    float* TMX = reinterpret_cast<float*>(IMGA + NP + 8);        // [NT] max of every point up to the end of thread t's
     float* TMN = TMX + NT;                                       // [NT] min of every point from the start of thread t's
     uint16_t* SID = reinterpret_cast<uint16_t*>(TMN + NT);       // [NP]
     uint16_t* WSP = SID + NP;                                    // [NP + 16] (holds the source-order ranks during the sort)
@@ -425,13 +425,21 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
         reinterpret_cast<float4*>(X + i0)[0] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(X + i0)[1] = make_float4(v[4], v[5], v[6], v[7]);
 #pragma unroll
-        for (int q = 0; q < CPT / 4; ++q) {
+        for (int q = 0; q < CPT / 4; ++q)
             reinterpret_cast<float4*>(Q + 1 + c0)[q] = make_float4(qv[4 * q], qv[4 * q + 1], qv[4 * q + 2], qv[4 * q + 3]);
-            reinterpret_cast<uint4*>(IMGP + 1 + c0)[q] = make_uint4(iv[4 * q], iv[4 * q + 1], iv[4 * q + 2], iv[4 * q + 3]);
+        // colour per POINT (sharp: both points of a pixel), indexed like X: the column after the last repeats it, which is
+        // the right sentinel's colour
+        if (SHARP) {
+            reinterpret_cast<uint4*>(IMGP + i0)[0] = make_uint4(iv[0], iv[0], iv[1], iv[1]);
+            reinterpret_cast<uint4*>(IMGP + i0)[1] = make_uint4(iv[2], iv[2], iv[3], iv[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < CPT / 4; ++q)
+                reinterpret_cast<uint4*>(IMGP + i0)[q] = make_uint4(iv[4 * q], iv[4 * q + 1], iv[4 * q + 2], iv[4 * q + 3]);
         }
         if (t == 0) { X[0] = (float)(-1.0 * W); Q[0] = 0.0f; IMGP[0] = iv[0]; }
         // vector path: the pad after the last column (the scalar path loaded it in place)
-        if (c0 + CPT == w && vec) IMGP[1 + w] = iv[CPT - 1];
+        if (c0 + CPT == w && vec) IMGP[npts - 1] = iv[CPT - 1];
     }
 
     CS_TICK(0);
@@ -682,11 +690,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     };
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
     const bool all_exact = (mode_flags & 8) != 0;
-    for (;;) {
-        int blk = 0;
-        if (lane == 0) blk = atomicAdd(&s_next, 1);
-        blk = __shfl_sync(0xffffffffu, blk, 0);
-        if (blk >= nblk) break;
+    for (int blk = wid; blk < nblk; blk += NW) {
         const int col = first + (blk << 5) + lane;
         const bool in = col < tw;
         uint32_t px = 0;

@@ -18,7 +18,7 @@ static int run_row(const uint8_t* img, const float* nd, int w, double div_px, do
     const int npts = (SHARP ? 2 * w : w) + 2, nsg = npts - 1;
     if (npts > 65535) return -1;
     std::vector<float> X(npts), SX(npts), Q(w + 2);
-    std::vector<uint32_t> ER(npts), IMG(w + 2);
+    std::vector<uint32_t> ER(npts), IMG(npts);
     std::vector<uint16_t> SID(npts), WIN(npts), START(w + 4), RNK(npts);
     X[0] = (float)(-1.0 * w);
     X[npts - 1] = (float)(2.0 * w);
@@ -34,9 +34,11 @@ static int run_row(const uint8_t* img, const float* nd, int w, double div_px, do
         Q[col + 1] = (float)fabs(cd);
         if (SHARP) { X[1 + 2 * col] = (float)(cx - 0.45); X[2 + 2 * col] = (float)(cx + 0.45); }
         else X[1 + col] = (float)cx;
-        IMG[col + 1] = (uint32_t)img[3 * col] | ((uint32_t)img[3 * col + 1] << 8) | ((uint32_t)img[3 * col + 2] << 16);
+        const uint32_t px = (uint32_t)img[3 * col] | ((uint32_t)img[3 * col + 1] << 8) | ((uint32_t)img[3 * col + 2] << 16);
+        if (SHARP) { IMG[1 + 2 * col] = px; IMG[2 + 2 * col] = px; }
+        else IMG[1 + col] = px;
     }
-    IMG[0] = IMG[1]; IMG[w + 1] = IMG[w];
+    IMG[0] = IMG[1]; IMG[npts - 1] = IMG[npts - 2];
     std::vector<int> order(npts);
     for (int i = 0; i < npts; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return X[a] < X[b]; });
