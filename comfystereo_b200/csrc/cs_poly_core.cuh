@@ -330,6 +330,76 @@ __device__ __noinline__ uint32_t exact_column_warp(const Tab& c, int col) {
     }
     return pack3((int)c0, (int)c1, (int)c2) | (ok ? 0u : kGaveUp);
 }
+
+// Up to four uncertified columns at once, eight lanes each (a column has 2..6 sub-intervals almost always): the FP64 work of
+// a row's few uncertified columns is one pass of one warp instead of one pass per column.  `cols[g]` is the column of lane
+// group g (lanes 8g..8g+7), g < ncols.  Returns the column's RGBX | kGaveUp to every lane of its group; groups whose
+// column has more than eight sub-intervals are reported in *big (bit g) and left to exact_column_warp.
+template <bool SHARP>
+__device__ __noinline__ uint32_t exact_columns_quad(const Tab& c, const uint16_t* cols, int ncols, uint32_t* big) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
+    const int col = (g < ncols) ? (int)cols[g] : -1;
+    int k0 = 0, cnt = 0;
+    if (col >= 0) { k0 = (int)c.START[col + 1] - 1; cnt = (int)c.START[col + 2] - 1 - k0 + 1; }
+    const bool is_big = cnt > 8;
+    const uint32_t bigbits = __ballot_sync(0xffffffffu, is_big);
+    *big = ((bigbits & 0x1u) ? 1u : 0u) | ((bigbits & 0x100u) ? 2u : 0u) | ((bigbits & 0x10000u) ? 4u : 0u) | ((bigbits & 0x1000000u) ? 8u : 0u);
+    if (is_big) cnt = 0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    bool have = false, bad = false;
+    if (j < cnt) {
+        const int k = k0 + j;
+        const double cold = (double)(col + c.t0), col1d = cold + 1.0;
+        const double pa = (double)c.SX[k], pb = (double)c.SX[k + 1];
+        const double from = ((pa > cold) ? pa : cold) + kEps;
+        const double to = ((pb < col1d) ? pb : col1d) - kEps;
+        const double sig = to - from;
+        const double ctr = from + 0.5 * sig;
+        const uint32_t inf = c.WSP[k];
+        int sp;
+        if (!(inf & kUnresolved) && sig > 0.0) {
+            sp = (int)inf;
+        } else {
+            sp = general_visit<SHARP>(c, col, k, ctr);
+            if (sp == -2) { bad = true; sp = -1; }
+        }
+        if (sp >= 0) {
+            const int cl = slot_col(pt_slot<SHARP>(sp), c.w), cr = slot_col(pt_slot<SHARP>(sp + 1), c.w);
+            const uint32_t pl = c.IMGP[sp];
+            double v0 = u8_to_f64(pl & 255u), v1 = u8_to_f64((pl >> 8) & 255u), v2 = u8_to_f64((pl >> 16) & 255u);
+            if (cl != cr) {
+                const double x0 = (double)c.X[sp];
+                const double x1 = (double)c.X[sp + 1];
+                const double den = round24_even(x1 - x0);
+                const double ip = (ctr - x0) / den;
+                const uint32_t pr = c.IMGP[sp + 1];
+                const double om = 1.0 - ip;
+                double a = v0 * om, b = u8_to_f64(pr & 255u) * ip;
+                v0 = a + b;
+                a = v1 * om; b = u8_to_f64((pr >> 8) & 255u) * ip;
+                v1 = a + b;
+                a = v2 * om; b = u8_to_f64((pr >> 16) & 255u) * ip;
+                v2 = a + b;
+            }
+            t0 = v0 * sig; t1 = v1 * sig; t2 = v2 * sig;
+            have = true;
+        }
+    }
+    const uint32_t badbits = __ballot_sync(0xffffffffu, bad), hv = __ballot_sync(0xffffffffu, have);
+    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    double c0 = 0.5, c1 = 0.5, c2 = 0.5;
+    for (int q = 0; q < maxcnt; ++q) {      // the float32-rounded running sums, in sub-interval order, per group
+        const int src = (lane & ~7) + q;
+        const double u0 = shfl_f64(t0, src), u1 = shfl_f64(t1, src), u2 = shfl_f64(t2, src);
+        if (q < cnt && ((hv >> src) & 1u)) {
+            c0 = round24_fp(c0 + u0);
+            c1 = round24_fp(c1 + u1);
+            c2 = round24_fp(c2 + u2);
+        }
+    }
+    const bool gbad = ((badbits >> (lane & ~7)) & 0xFFu) != 0u;
+    return pack3((int)c0, (int)c1, (int)c2) | (gbad ? kGaveUp : 0u);
+}
 #endif
 
 // ------------------------------------------------------------------ float32 path

@@ -705,11 +705,23 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     bool give_up = false;
     {
         const int nflag = s_nflag;
-        for (int q = wid; q < nflag; q += NW) {     // one column per warp at a time
-            const int col = LIST[q];
-            uint32_t px = poly::exact_column_warp<SHARP>(s_tab, col);
-            if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
-            if (lane == 0) emit(col, px);
+        for (int base = 4 * wid; base < nflag; base += 4 * NW) {     // four columns per warp at a time, eight lanes each
+            const int ncols = min(4, nflag - base);
+            uint32_t big = 0;
+            uint32_t px = poly::exact_columns_quad<SHARP>(s_tab, LIST + base, ncols, &big);
+            const int gq = lane >> 3;
+            if (gq < ncols && !((big >> gq) & 1u)) {
+                if (px & poly::kGaveUp) { give_up = true; px &= ~poly::kGaveUp; }
+                if ((lane & 7) == 0) emit(LIST[base + gq], px);
+            }
+            while (big) {                                         // columns with more than eight sub-intervals: a warp each
+                const int gb = __ffs(big) - 1;
+                big &= big - 1;
+                const int col = LIST[base + gb];
+                uint32_t pb = poly::exact_column_warp<SHARP>(s_tab, col);
+                if (pb & poly::kGaveUp) { give_up = true; pb &= ~poly::kGaveUp; }
+                if (lane == 0) emit(col, pb);
+            }
         }
 #ifdef CS_POLY_TIMING
         if (t == 0) { atomicAdd(&g_poly_ticks[12], (unsigned long long)nflag); atomicAdd(&g_poly_ticks[13], 1ull); }
