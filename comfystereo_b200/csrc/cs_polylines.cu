@@ -368,8 +368,6 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     const int c0 = t * CPT, i0 = 1 + 8 * t;
     float v[8];
     {
-        float scale;
-        const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
         const float* dep = a.depth[eye] + row_off + s0;
         const uint32_t* img = a.image_u8 + row_off + s0;
         float dv[CPT];
@@ -392,6 +390,9 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
                 iv[j] = in ? __ldg(img + cc) : 0u;
             }
         }
+        // (after the row's loads are in flight: the frame statistics are another dependent global load)
+        float scale;
+        const Normalizer norm = pl_normalizer(a, eye, frame, &scale);
         const double div_px = a.eye[eye].div_px, sep_px = a.eye[eye].sep_px;
         const double base = (double)(c0 + s0) + 0.5;
         float qv[CPT];
@@ -705,7 +706,8 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     bool give_up = false;
     {
         const int nflag = s_nflag;
-        for (int base = 4 * wid; base < nflag; base += 4 * NW) {     // four columns per warp at a time, eight lanes each
+        // (from the last warp down: with round-robin blocks the first warps have swept one block more)
+        for (int base = 4 * (NW - 1 - wid); base < nflag; base += 4 * NW) {     // four columns per warp at a time, eight lanes each
             const int ncols = min(4, nflag - base);
             uint32_t big = 0;
             uint32_t px = poly::exact_columns_quad<SHARP>(s_tab, LIST + base, ncols, &big);
