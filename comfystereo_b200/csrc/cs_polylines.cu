@@ -353,12 +353,12 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     uint16_t* START = LIST + NP;                                 // [SCAP + 8]
     __shared__ float s_wa[32], s_wb[32];
     __shared__ int s_wr[32];
-    __shared__ int s_nslow, s_nhard, s_next, s_nflag;
+    __shared__ int s_nslow, s_nhard, s_nflag;
     __shared__ float s_q255[256];     // k / 255.0f (GS:365-378), for the fused composed output
     __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
     for (int k = t; k < 256; k += NT) s_q255[k] = (float)k / 255.0f;
     if (t == 0) {
-        s_nslow = 0; s_nhard = 0; s_next = 0; s_nflag = 0;
+        s_nslow = 0; s_nhard = 0; s_nflag = 0;
         s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;
         s_tab.START = START; s_tab.w = w; s_tab.npts = npts; s_tab.nsg = nsg; s_tab.t0 = t0;
     }
@@ -673,9 +673,10 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     __syncthreads();
     CS_TICK(7);
 
-    // ---- E: sweep.  Warps take 32-column blocks from a shared counter (blocks inside folds cost several times more).
-    // Columns the float32 path cannot certify are listed and redone afterwards, all at once: inside the sweep each of
-    // them would stall its whole warp for longer than a block takes, and the slowest warp sets the CTA's lifetime.
+    // ---- E: sweep.  Warps take the 32-column blocks round-robin (a shared counter balanced the blocks inside folds, which
+    // cost several times more, but its atomic + shuffle was 6 % of the kernel's instructions and the balance buys nothing:
+    // the other CTA of the SM fills the gaps).  Columns the float32 path cannot certify are listed and redone afterwards,
+    // four per warp pass: inside the sweep each of them would stall its whole warp for longer than a block takes.
     uint32_t* out = a.fused_stereo ? nullptr : a.out[eye] + row_off + t0;
     const uint64_t pol = policy_evict_first();
     // one finished pixel: the RGBX8 eye image, or (fused) its place in the composed float32 tensor and the black-pixel mask
