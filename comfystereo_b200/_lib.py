@@ -61,6 +61,7 @@ SIGNATURES = {
     "cs_warp_fill": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _SZ, _P]),
     "cs_warp_fill_scratch_bytes": (_SZ, [_I, _I, _I]),
     "cs_forward_warp": (_I, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _SZ, _P]),
+    "cs_forward_warp_scratch_bytes": (_SZ, [_I, _I, _I]),
     "cs_forward_warp_mesh": (_I, [_P, _P, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _SZ, _P]),
     "cs_forward_warp_mesh_scratch_bytes": (_SZ, [_I, _I, _I]),
     "cs_quantize_image": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -130,6 +130,7 @@ struct Workspace {
     uint32_t* eye_out[2];
     void* warp_scratch;
     size_t warp_scratch_bytes;
+    void* row_scratch;       // GPU Warp rows too wide for shared memory (gpuwarp_row_scratch_bytes)
     size_t total;
 };
 
@@ -163,6 +164,7 @@ static Workspace carve(const cs_params* p, int chunk, int h, int w, void* base) 
         ws.warp_scratch_bytes = mesh_keep_bytes(chunk, h, w);   // the culled topology, one per sub-batch and eye
         ws.warp_scratch = take(ws.warp_scratch_bytes);
     }
+    if (!cpu && gpuwarp_row_scratch_bytes(w)) ws.row_scratch = take(gpuwarp_row_scratch_bytes(w));
     ws.total = off;
     return ws;
 }
@@ -258,6 +260,7 @@ static int run_chunk(const cs_params* p, const float* image, const float* depth,
         g.expo = (float)p->stereo_offset_exponent;
         g.conv = (float)p->convergence_point;
         g.stereo = stereo; g.mask = mask;
+        g.row_scratch = ws.row_scratch; g.row_scratch_stride = gpuwarp_row_scratch_stride(w);
         if (p->fill == CS_FILL_GPU_WARP_MESH) {
             g.keep = (uint8_t*)ws.warp_scratch;
             CS_CUDA(launch_meshwarp(g, s), "meshwarp");
@@ -472,12 +475,18 @@ int cs_warp_fill(const uint8_t* image_u8, const float* depth, int n, int h, int 
     return CS_OK;
 }
 
+size_t cs_forward_warp_scratch_bytes(int n, int h, int w) {
+    if (n < 1 || h < 1 || w < 1) return 0;
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(gpuwarp_row_scratch_bytes(w));
+}
+
 int cs_forward_warp(const float* image, const float* depth, int n, int h, int w, double div_px, double sep_px,
                     double exponent, double convergence, float* warped, float* mask, void* scratch,
                     size_t scratch_bytes, void* stream) {
     if (!image || !depth || !warped || !mask || !scratch || n < 1 || h < 1 || w < 1)
         return fail(CS_ERR_ARG, "cs_forward_warp: bad argument");
-    if (scratch_bytes < (size_t)n * sizeof(FrameStats)) return fail(CS_ERR_WORKSPACE, "cs_forward_warp: scratch too small");
+    if (scratch_bytes < cs_forward_warp_scratch_bytes(n, h, w)) return fail(CS_ERR_WORKSPACE, "cs_forward_warp: scratch too small");
+    if (w > 24000) return fail(CS_ERR_UNSUPPORTED, "cs_forward_warp: width %d exceeds the 24000-pixel row capacity", w);
     cudaStream_t s = (cudaStream_t)stream;
     FrameStats* st = (FrameStats*)scratch;
     CS_CUDA(launch_init_stats(st, n, s), "init_stats");
@@ -493,13 +502,15 @@ int cs_forward_warp(const float* image, const float* depth, int n, int h, int w,
     g.eye[1].passthrough = 1;
     g.expo = (float)exponent; g.conv = (float)convergence;
     g.stereo = warped; g.mask = mask;
+    g.row_scratch = (char*)scratch + align_up((size_t)n * sizeof(FrameStats));
+    g.row_scratch_stride = gpuwarp_row_scratch_stride(w);
     CS_CUDA(launch_gpuwarp(g, s), "gpuwarp");
     return CS_OK;
 }
 
 size_t cs_forward_warp_mesh_scratch_bytes(int n, int h, int w) {
     if (n < 1 || h < 1 || w < 1) return 0;
-    return align_up((size_t)n * sizeof(FrameStats)) + align_up(mesh_keep_bytes(n, h, w));
+    return align_up((size_t)n * sizeof(FrameStats)) + align_up(mesh_keep_bytes(n, h, w)) + align_up(gpuwarp_row_scratch_bytes(w));
 }
 
 int cs_forward_warp_mesh(const float* image, const float* depth, int n, int h, int w, double div_px, double sep_px,
@@ -509,7 +520,7 @@ int cs_forward_warp_mesh(const float* image, const float* depth, int n, int h, i
         return fail(CS_ERR_ARG, "cs_forward_warp_mesh: bad argument");
     if (scratch_bytes < cs_forward_warp_mesh_scratch_bytes(n, h, w))
         return fail(CS_ERR_WORKSPACE, "cs_forward_warp_mesh: scratch too small");
-    if (w > 9000) return fail(CS_ERR_UNSUPPORTED, "cs_forward_warp_mesh: width %d exceeds the 9000-pixel row capacity", w);
+    if (w > 24000) return fail(CS_ERR_UNSUPPORTED, "cs_forward_warp_mesh: width %d exceeds the 24000-pixel row capacity", w);
     cudaStream_t s = (cudaStream_t)stream;
     FrameStats* st = (FrameStats*)scratch;
     CS_CUDA(launch_init_stats(st, n, s), "init_stats");
@@ -526,6 +537,8 @@ int cs_forward_warp_mesh(const float* image, const float* depth, int n, int h, i
     g.expo = (float)exponent; g.conv = (float)convergence;
     g.stereo = warped; g.mask = mask;
     g.keep = (uint8_t*)scratch + align_up((size_t)n * sizeof(FrameStats));
+    g.row_scratch = (char*)g.keep + align_up(mesh_keep_bytes(n, h, w));
+    g.row_scratch_stride = gpuwarp_row_scratch_stride(w);
     CS_CUDA(launch_meshwarp(g, s), "meshwarp");
     return CS_OK;
 }
@@ -566,7 +579,7 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
         // Polylines: rows of any width are tiled (only the 16-bit point indices of the sequential fallback bound them);
         // the other techniques keep one row per CTA in shared memory
         const bool plus = p->fill == CS_FILL_HYBRID_EDGE_PLUS;
-        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (is_gpu_warp(p->fill) ? 9000 : 16000));
+        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (is_gpu_warp(p->fill) ? 24000 : 16000));
         if (w > wmax)
             return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
                         "(one row per CTA in shared memory)", w, wmax);

@@ -85,10 +85,10 @@ __device__ __forceinline__ float gw_offset(const DepthNorm& nm, float dv, float 
     return m + sep_px;
 }
 
-template <int TPB>   // CTA size the kernel is compiled for (register budget): 256, or 512 for rows that leave room for two CTAs per SM
-__global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
-    extern __shared__ __align__(16) float smem_f[];
-    const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
+// One (row, frame) of the scatter warp; `smem_f` is the row's state: shared memory, or -- for rows too wide for it -- the
+// CTA's slice of a global scratch buffer (same code: the atomics and barriers work on either).
+__device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, const int frame, float* smem_f) {
+    const int w = a.w, h = a.h;
     const int nwords = (w + 31) >> 5;
     float* ndv = smem_f;
     float* po = ndv + w;
@@ -305,6 +305,23 @@ __global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
     for (int x = threadIdx.x; x < w; x += blockDim.x) mrow[x] = ((ubits[x >> 5] >> (x & 31)) & 1u) ? 1.0f : 0.0f;
 }
 
+template <int TPB>   // CTA size the kernel is compiled for (register budget): 256, or 512 for rows that leave room for two CTAs per SM
+__global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    gpuwarp_row(a, blockIdx.x, blockIdx.y, smem_f);
+}
+
+// Rows whose state does not fit a CTA's shared memory (wider than ~9000 px: 16K panoramas): a few CTAs per SM walk the
+// (row, frame) items with the state in their slice of a global scratch buffer.  Slow next to the shared-memory kernel, but
+// the reference has no width limit either.
+__global__ void __launch_bounds__(512) k_gpuwarp_wide(const GpuWarpArgs a) {
+    float* mem = reinterpret_cast<float*>(reinterpret_cast<char*>(a.row_scratch) + (size_t)blockIdx.x * a.row_scratch_stride);
+    for (int item = blockIdx.x; item < a.h * a.n; item += gridDim.x) {
+        gpuwarp_row(a, item % a.h, item / a.h, mem);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Mesh warp: forward_warp_mesh (SIG:453-689), what 'GPU Warp (Fast)' runs when the host has ModernGL (SIG:1068-1071).
 //
@@ -373,10 +390,9 @@ __global__ void __launch_bounds__(256) k_mesh_keep(const GpuWarpArgs a) {
     for (int x = threadIdx.x; x + 1 < w; x += blockDim.x) out[x] = kb[x];
 }
 
-// One CTA per (output row, frame), both eyes in turn, composed into the final stereo layout like k_gpuwarp.
-__global__ void __launch_bounds__(512) k_meshwarp(const GpuWarpArgs a) {
-    extern __shared__ __align__(16) float smem_f[];
-    const int w = a.w, h = a.h, y = blockIdx.x, frame = blockIdx.y;
+// One (output row, frame), both eyes in turn, composed into the final stereo layout like k_gpuwarp.
+__device__ __forceinline__ void meshwarp_row(const GpuWarpArgs& a, const int y, const int frame, float* smem_f) {
+    const int w = a.w, h = a.h;
     const int nwords = (w + 31) >> 5;
     unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_f);   // z-buffer: ordered depth << 32 | ~draw order
     float* X0 = reinterpret_cast<float*>(key + w);
@@ -547,6 +563,29 @@ __global__ void __launch_bounds__(512) k_meshwarp(const GpuWarpArgs a) {
     for (int x = threadIdx.x; x < w; x += blockDim.x) mrow[x] = ((ubits[x >> 5] >> (x & 31)) & 1u) ? 1.0f : 0.0f;
 }
 
+__global__ void __launch_bounds__(512) k_meshwarp(const GpuWarpArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    meshwarp_row(a, blockIdx.x, blockIdx.y, smem_f);
+}
+__global__ void __launch_bounds__(512) k_meshwarp_wide(const GpuWarpArgs a) {      // see k_gpuwarp_wide
+    float* mem = reinterpret_cast<float*>(reinterpret_cast<char*>(a.row_scratch) + (size_t)blockIdx.x * a.row_scratch_stride);
+    for (int item = blockIdx.x; item < a.h * a.n; item += gridDim.x) {
+        meshwarp_row(a, item % a.h, item / a.h, mem);
+        __syncthreads();
+    }
+}
+
+// global row scratch for rows too wide for shared memory: bytes per CTA and CTAs (both warps share the geometry)
+constexpr size_t kRowSmemLimit = 227 * 1024;
+static size_t gw_row_bytes(int w) {
+    const size_t nwords = (size_t)(w + 31) >> 5;
+    const size_t b = (size_t)w * 24 + 64 + nwords * 8 + (size_t)w + 16;     // k_gpuwarp's layout, the larger of the two
+    return (b + 255) & ~(size_t)255;
+}
+static int gw_wide_ctas() { return 2 * sm_count(); }
+size_t gpuwarp_row_scratch_stride(int w) { return gw_row_bytes(w); }
+size_t gpuwarp_row_scratch_bytes(int w) { return gw_row_bytes(w) > kRowSmemLimit ? gw_row_bytes(w) * (size_t)gw_wide_ctas() : 0; }
+
 size_t mesh_keep_bytes(int n, int h, int w) { return (size_t)2 * n * (h > 1 ? h - 1 : 1) * (w > 1 ? w - 1 : 1); }
 
 cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
@@ -563,7 +602,14 @@ cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
         count_launch();
     }
     const size_t smem = (size_t)a.w * 24 + (size_t)nwords * 8;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (gw_row_bytes(a.w) > kRowSmemLimit) {     // (the same threshold as the scatter warp: one scratch geometry for both)
+        if (!a.row_scratch || a.row_scratch_stride < gw_row_bytes(a.w)) return cudaErrorInvalidValue;
+        prof_begin(K_GPUWARP, s);
+        k_meshwarp_wide<<<gw_wide_ctas(), 512, 0, s>>>(a);
+        prof_end(K_GPUWARP, s);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_meshwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // a wide row's shared memory (24 B per column) leaves room for two CTAs per SM: make them 512 threads, like k_gpuwarp
     const int tpb = smem > 56 * 1024 ? 512 : 256;
@@ -577,7 +623,14 @@ cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
     size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8 + (size_t)a.w + 16;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (gw_row_bytes(a.w) > kRowSmemLimit) {
+        if (!a.row_scratch || a.row_scratch_stride < gw_row_bytes(a.w)) return cudaErrorInvalidValue;
+        prof_begin(K_GPUWARP, s);
+        k_gpuwarp_wide<<<gw_wide_ctas(), 512, 0, s>>>(a);
+        prof_end(K_GPUWARP, s);
+        count_launch();
+        return cudaGetLastError();
+    }
     // a row's shared memory (25 B per column) limits the CTAs per SM: keep ~32 warps resident by widening the CTA
     const bool wide = smem > 56 * 1024;
     if (smem > 48 * 1024) {

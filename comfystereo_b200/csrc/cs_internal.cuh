@@ -238,7 +238,11 @@ struct GpuWarpArgs {
     float* stereo;             // final layout
     float* mask;               // [n][h][w]
     uint8_t* keep;             // mesh warp only: mesh_keep_bytes(n, h, w) of scratch for the culled topology
+    void* row_scratch;         // rows too wide for shared memory only: gpuwarp_row_scratch_bytes(w) of global scratch ...
+    size_t row_scratch_stride; // ... and the bytes of one CTA's slice (gpuwarp_row_scratch_stride(w))
 };
+size_t gpuwarp_row_scratch_bytes(int w);      // 0 while a row's state fits a CTA's shared memory (up to ~9200 columns)
+size_t gpuwarp_row_scratch_stride(int w);
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s);
 // forward_warp_mesh (SIG:453-689): same arguments, plus the keep scratch
 size_t mesh_keep_bytes(int n, int h, int w);

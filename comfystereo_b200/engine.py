@@ -232,7 +232,7 @@ def forward_warp_device(image, depth, div_px, sep_px, exponent, convergence, mes
     image [n,h,w,3] float32 CUDA, depth [n,h,w] as given.  Returns (warped [n,h,w,3], mask float32 [n,h,w])."""
     n, h, w = depth.shape
     lib = _lib.lib()
-    nb = lib.cs_forward_warp_mesh_scratch_bytes(n, h, w) if mesh else 32 * n
+    nb = lib.cs_forward_warp_mesh_scratch_bytes(n, h, w) if mesh else lib.cs_forward_warp_scratch_bytes(n, h, w)
     scratch = torch.empty(nb, dtype=torch.uint8, device=depth.device)
     warped = torch.empty((n, h, w, 3), dtype=torch.float32, device=depth.device)
     mask = torch.empty((n, h, w), dtype=torch.float32, device=depth.device)

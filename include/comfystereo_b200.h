@@ -161,10 +161,12 @@ CS_API size_t cs_warp_fill_scratch_bytes(int n, int h, int w);
  * warp when moderngl is absent).  image [n][h][w][3] float32 (NHWC; the reference's NCHW permute is
  * a view), depth [n][h][w] as given (divided by 255 when any frame's max > 1, SIG:314-316).
  * warped [n][h][w][3], mask [n][h][w] = the PRE-fill "unfilled" map (1.0 / 0.0).
- * scratch: at least 32*n bytes. */
+ * scratch: cs_forward_warp_scratch_bytes(n, h, w) -- the per-frame statistics, plus global row state for rows too wide
+ * for a CTA's shared memory (beyond ~9200 columns; up to 24000). */
 CS_API int cs_forward_warp(const float *image, const float *depth, int n, int h, int w, double div_px,
                     double sep_px, double exponent, double convergence, float *warped, float *mask,
                     void *scratch, size_t scratch_bytes, void *stream);
+CS_API size_t cs_forward_warp_scratch_bytes(int n, int h, int w);
 
 /* The same for the ModernGL variant: replaces forward_warp_mesh(image, depth, divergence_px, separation_px,
  * stereo_offset_exponent, convergence_point), SIG:453-689 -- the mesh of per-pixel vertices, culled with the

@@ -104,7 +104,7 @@ def forward_warp(img_hwc, depth, div_px, sep_px, expo, conv):
     n, h, w = td.shape
     out = torch.empty_like(ti)
     mask = torch.empty((n, h, w), dtype=torch.float32, device=dev())
-    scratch = torch.empty(32 * n + 256, dtype=torch.uint8, device=dev())
+    scratch = torch.empty(_lib.lib().cs_forward_warp_scratch_bytes(n, h, w), dtype=torch.uint8, device=dev())
     _lib.check(_lib.lib().cs_forward_warp(ti.data_ptr(), td.data_ptr(), n, h, w, float(div_px), float(sep_px),
                                           float(expo), float(conv), out.data_ptr(), mask.data_ptr(),
                                           scratch.data_ptr(), scratch.numel(), stream()))

@@ -358,11 +358,12 @@ def test_polylines_sequential_fallback_with_global_tables(oracle):
         assert np.array_equal(got, want), fill
 
 
-@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 32766), ("GPU Warp (Fast)", 9000), ("Fill - Naive", 16000),
+@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 32766), ("GPU Warp (Fast)", 24000), ("Fill - Naive", 16000),
                                        ("Imperfect fill - Hybrid Edge", 16000)])
 def test_row_capacity_limits(oracle, fill, wmax):
-    """The row techniques keep one row per CTA in shared memory and have a documented maximum width; Polylines is bounded
-    only by the 16-bit point indices of its sequential fallback (32766 px sharp, 65533 px soft).  At the limit the node
+    """The row techniques keep one row per CTA in shared memory and have a documented maximum width (GPU Warp keeps rows
+    beyond ~9200 px in global scratch, up to 24000 px); Polylines is bounded only by the 16-bit point indices of its
+    sequential fallback (32766 px sharp, 65533 px soft).  At the limit the node
     still matches the oracle, one step beyond it the library refuses up front (CS_ERR_UNSUPPORTED)."""
     from comfystereo_b200 import StereoImageNode
     from comfystereo_b200._lib import CsError

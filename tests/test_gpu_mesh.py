@@ -139,11 +139,25 @@ def test_node_with_mesh_warp(gu, oracle, monkeypatch):
 
 def test_mesh_width_limit_and_wide_rows(gu, oracle):
     from comfystereo_b200 import engine, _lib
-    h, w = 4, 8192                                 # > 48 KB of shared memory per row: the opt-in path
-    img = syn.make_image(1, h, w, seed=5)
-    d = (syn.make_depth(1, h, w, "scene", seed=6)[..., 0] / np.float32(255)).astype(np.float32)
-    warped, mask = _warp(img, d, 160.0, 0.0, 1.0, 0.5)
-    ow, om = oracle.meshwarp_batch(img.transpose(0, 3, 1, 2), d, 160.0, 0.0, 1.0, 0.5)
-    assert np.array_equal(mask, om) and np.array_equal(warped.transpose(0, 3, 1, 2), ow)
-    with pytest.raises(_lib.CsError, match="9000"):
-        engine.forward_warp_device(torch.zeros(1, 2, 9001, 3).cuda(), torch.zeros(1, 2, 9001).cuda(), 1.0, 0.0, 1.0, 0.5, mesh=True)
+    # 8192: > 48 KB of shared memory per row (the opt-in path, 512-thread CTAs); 16384: the row state no longer fits a CTA's
+    # shared memory and lives in global scratch (k_meshwarp_wide) -- a 16K panorama row
+    for h, w, div_px in ((4, 8192, 160.0), (3, 16384, 300.0)):
+        img = syn.make_image(2, h, w, seed=5)
+        d = (syn.make_depth(2, h, w, "scene", seed=6)[..., 0] / np.float32(255)).astype(np.float32)
+        warped, mask = _warp(img, d, div_px, 0.0, 1.0, 0.5)
+        ow, om = oracle.meshwarp_batch(img.transpose(0, 3, 1, 2), d, div_px, 0.0, 1.0, 0.5)
+        assert np.array_equal(mask, om) and np.array_equal(warped.transpose(0, 3, 1, 2), ow), w
+    with pytest.raises(_lib.CsError, match="24000"):
+        engine.forward_warp_device(torch.zeros(1, 2, 24001, 3).cuda(), torch.zeros(1, 2, 24001).cuda(), 1.0, 0.0, 1.0, 0.5, mesh=True)
+
+
+def test_scatter_warp_16k_rows_in_global_scratch(gu, oracle):
+    """forward_warp_gpu on rows wider than a CTA's shared memory can hold (k_gpuwarp_wide): same result as the oracle."""
+    h, w = 3, 16384
+    img = syn.make_image(2, h, w, seed=8)
+    d = (syn.make_depth(2, h, w, "scene", seed=9)[..., 0] / np.float32(255)).astype(np.float32)
+    warped, mask = gu.forward_warp(img, d, 250.0, -3.0, 2.0, 0.5)
+    for b in range(2):
+        ow, om = oracle.gpuwarp_eye(np.ascontiguousarray(img[b].transpose(2, 0, 1)), d[b], 250.0, -3.0, 2.0, 0.5)
+        assert np.array_equal(mask[b], om)
+        assert np.abs(warped[b].transpose(2, 0, 1) - ow).max() <= 1e-6
