@@ -579,7 +579,7 @@ int cs_stereo_batch(const cs_params* p, const float* image, const float* depth, 
         // Polylines: rows of any width are tiled (only the 16-bit point indices of the sequential fallback bound them);
         // the other techniques keep one row per CTA in shared memory
         const bool plus = p->fill == CS_FILL_HYBRID_EDGE_PLUS;
-        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (is_gpu_warp(p->fill) ? 24000 : 16000));
+        const int wmax = sharp ? 32766 : (soft && !plus ? 65533 : (is_gpu_warp(p->fill) ? 24000 : 18000));
         if (w > wmax)
             return fail(CS_ERR_UNSUPPORTED, "cs_stereo_batch: width %d exceeds the %d-pixel row capacity of this technique "
                         "(one row per CTA in shared memory)", w, wmax);

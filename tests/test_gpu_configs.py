@@ -316,7 +316,7 @@ def test_very_wide_rows(oracle, fill):
     CTAs there (launch_warp_rows / launch_hybrid); same results as the oracle."""
     import gpu_util as gu
     rng = np.random.default_rng(77)
-    for h, w in ((3, 7700), (2, 15990)):     # 15990: close to the 16000-column capacity of these techniques
+    for h, w in ((3, 7700), (2, 16384)):     # 16384: a 16K panorama row, close to the 18000-column capacity of these techniques
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         d = (syn.make_depth(1, h, w, "scene", seed=5, channels=1)[0, ..., 0] * np.float32(255)).astype(np.float32)
         got = gu.warp_fill(img, d, fill, 1.5, 0.2, 2.0, 0.5)[..., :3]
@@ -358,8 +358,8 @@ def test_polylines_sequential_fallback_with_global_tables(oracle):
         assert np.array_equal(got, want), fill
 
 
-@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 32766), ("GPU Warp (Fast)", 24000), ("Fill - Naive", 16000),
-                                       ("Imperfect fill - Hybrid Edge", 16000)])
+@pytest.mark.parametrize("fill,wmax", [("Fill - Polylines Sharp", 32766), ("GPU Warp (Fast)", 24000), ("Fill - Naive", 18000),
+                                       ("Fill - Naive interpolating", 18000), ("Imperfect fill - Hybrid Edge", 18000)])
 def test_row_capacity_limits(oracle, fill, wmax):
     """The row techniques keep one row per CTA in shared memory and have a documented maximum width (GPU Warp keeps rows
     beyond ~9200 px in global scratch, up to 24000 px); Polylines is bounded only by the 16-bit point indices of its
