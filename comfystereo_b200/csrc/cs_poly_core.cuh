@@ -499,67 +499,50 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
 template <bool SHARP>
 CS_HD uint32_t classify_interval(const Tab& c, int k) {
     constexpr int kMaxCand = 4;
-    int cnt = 0, j0 = 0, j1 = 0, j2 = 0, j3 = 0;
-    for (int j = k; j >= 0; --j) {
-        const uint32_t er = c.ER[j];
-        if ((int)(er >> 16) <= k) break;            // nothing at or before j reaches past point k
-        if ((int)(er & 0xFFFFu) > k) {
-            if (cnt == 0) j0 = j; else if (cnt == 1) j1 = j; else if (cnt == 2) j2 = j; else if (cnt == 3) j3 = j;
-            ++cnt;
-        }
-    }
-    const uint32_t own = (uint32_t)c.SID[k];
-    if (cnt == 1) return (uint32_t)c.SID[j0];
-    if (cnt < 1 || cnt > kMaxCand) return own | kUnresolved;
     // Interpolated closeness is linear in the centre, so a candidate that leads every other one at both ends of the
     // interval leads at every centre inside.  The reference also requires 0 < ip < 1; ip > 0 always holds for an active
     // segment, and ip < 1 can only fail (float32 rounding of x1 - x0) for long segments that end at or just beyond this
     // interval's right point -- those leave the interval unresolved, to be decided per visit in FP64.
+    // One pass over the candidates as the walk finds them, with running statistics instead of a table: the leader at the
+    // left end (largest closeness there), the runner-up's value, and the two largest values at the right end.
     const float av = c.SX[k], bv = c.SX[k + 1];
-    float lo[kMaxCand], hi[kMaxCand];
-    uint32_t sps[kMaxCand];
+    int cnt = 0, obest = -1, ohi1 = -1;
+    float lo1 = -1.0f, lo2 = -1.0f, hib = -1.0f, hi1 = -1.0f, hi2 = -1.0f;     // closeness is >= 0: -1 is "none"
+    uint32_t spb = 0, first = 0;
     bool safe = true;
     float qmax = 0.0f;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int q = 0; q < kMaxCand; ++q) {
-        const int j = (q == 0) ? j0 : (q == 1 ? j1 : (q == 2 ? j2 : j3));
-        lo[q] = -1.0f; hi[q] = -1.0f; sps[q] = 0;
-        if (q < cnt) {
+    for (int j = k; j >= 0; --j) {
+        const uint32_t er = c.ER[j];
+        if ((int)(er >> 16) <= k) break;            // nothing at or before j reaches past point k
+        if ((int)(er & 0xFFFFu) > k) {
             const int sp = (int)c.SID[j];
+            if (cnt == 0) first = (uint32_t)sp;
             const float q0 = c.Q[pt_slot<SHARP>(sp)], q1 = c.Q[pt_slot<SHARP>(sp + 1)];
             const float x0 = c.SX[j], x1 = c.X[sp + 1];
             const float d = x1 - x0;
-            safe = safe && (d < 2.0f || (x1 - bv) > d * 1.2e-7f);
+            safe = safe && d > 0.0f && (d < 2.0f || (x1 - bv) > d * 1.2e-7f);
             float l = q0, h = q0;
             if (q0 != q1) {     // (segments of constant closeness -- the two points of one pixel -- need none of this)
                 const float r = fast_rcp(d);
                 l = q0 + (av - x0) * r * (q1 - q0);
                 h = q0 + (bv - x0) * r * (q1 - q0);
             }
-            lo[q] = l; hi[q] = h; sps[q] = (uint32_t)sp;
+            if (l > lo1) { lo2 = lo1; lo1 = l; hib = h; spb = (uint32_t)sp; obest = cnt; }
+            else if (l > lo2) lo2 = l;
+            if (h > hi1) { hi2 = hi1; hi1 = h; ohi1 = cnt; }
+            else if (h > hi2) hi2 = h;
             qmax = fmaxf(qmax, fmaxf(q0, q1));
+            ++cnt;
         }
     }
-    const float margin = 1e-3f + 1e-4f * qmax;
+    const uint32_t own = (uint32_t)c.SID[k];
+    if (cnt == 1) return first;
+    if (cnt < 1 || cnt > kMaxCand) return own | kUnresolved;
     // the leader at the left end must lead every other candidate by the margin at both ends
-    int best = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int q = 1; q < kMaxCand; ++q)
-        if (q < cnt && lo[q] > lo[best]) best = q;
-    const float bl = (best == 0) ? lo[0] : (best == 1 ? lo[1] : (best == 2 ? lo[2] : lo[3]));
-    const float bh = (best == 0) ? hi[0] : (best == 1 ? hi[1] : (best == 2 ? hi[2] : hi[3]));
-    const uint32_t bs = (best == 0) ? sps[0] : (best == 1 ? sps[1] : (best == 2 ? sps[2] : sps[3]));
-    bool lead = safe;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int q = 0; q < kMaxCand; ++q)
-        if (q < cnt && q != best) lead = lead && (bl > lo[q] + margin) && (bh > hi[q] + margin);
-    return lead ? bs : (own | kUnresolved);
+    const float margin = 1e-3f + 1e-4f * qmax;
+    const float others_hi = (ohi1 == obest) ? hi2 : hi1;
+    const bool lead = safe && (lo1 > lo2 + margin) && (hib > others_hi + margin);
+    return lead ? spb : (own | kUnresolved);
 }
 
 }  // namespace poly
