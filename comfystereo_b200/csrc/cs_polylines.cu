@@ -680,15 +680,16 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     uint32_t* out = a.fused_stereo ? nullptr : a.out[eye] + row_off + t0;
     const uint64_t pol = policy_evict_first();
     // one finished pixel: the RGBX8 eye image, or (fused) its place in the composed float32 tensor and the black-pixel mask
+    const int64_t o_row = a.fused_stereo ? fused_index(a, eye, frame, y, t0) : 0;      // the row's place in the composed tensors
+    float* const dst_row = a.fused_stereo + o_row * 3;
+    float* const msk_row = a.fused_mask + o_row;
     auto emit = [&](int col, uint32_t px) {
         if (out) { out[col] = px; return; }
-        const int64_t o = fused_index(a, eye, frame, y, col + t0);
-        const uint32_t r = px & 255u, gch = (px >> 8) & 255u, b = (px >> 16) & 255u;
-        float* dst = a.fused_stereo + o * 3;
-        st_stream_f1(dst, s_q255[r], pol);
-        st_stream_f1(dst + 1, s_q255[gch], pol);
-        st_stream_f1(dst + 2, s_q255[b], pol);
-        st_stream_f1(a.fused_mask + o, (r + gch + b == 0u) ? 1.0f : 0.0f, pol);
+        float* dst = dst_row + col * 3;
+        st_stream_f1(dst, s_q255[px & 255u], pol);
+        st_stream_f1(dst + 1, s_q255[(px >> 8) & 255u], pol);
+        st_stream_f1(dst + 2, s_q255[(px >> 16) & 255u], pol);
+        st_stream_f1(msk_row + col, ((px & 0x00FFFFFFu) == 0u) ? 1.0f : 0.0f, pol);
     };
     const int nblk = (own + 31) >> 5, first = tw - own;   // the tile's own columns are the last `own` bucket columns
     const bool all_exact = (mode_flags & 8) != 0;
