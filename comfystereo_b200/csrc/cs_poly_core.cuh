@@ -450,7 +450,7 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
     const int k0 = (int)c.START[col + 1] - 1, k1 = (int)c.START[col + 2] - 1;
     const float cf = (float)(col + c.t0), cf1 = cf + 1.0f;
     float a0 = 0.5f, a1 = 0.5f, a2 = 0.5f;
-    float pa = c.SX[k0];
+    float pa = c.SX[k0], dmin = 1.0f;
     uint32_t bad = 0;
     // (not unrolled: the trip count differs from lane to lane, and an unrolled body plus a remainder loop makes the warp
     // execute both for the longest lane; fetching sub-interval k + 1's tables while k is accumulated -- software
@@ -463,8 +463,10 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
         const uint32_t inf = c.WSP[k];
         const float fromp = fmaxf(pa, cf), top = fminf(pb, cf1);
         const float d = top - fromp;
-        // no pre-resolved winner, or an interval too short to have a centre strictly inside it
-        bad |= inf | ((d >= 1e-6f) ? 0u : kUnresolved);
+        // no pre-resolved winner (bit 15), or -- checked once, on the minimum -- an interval too short to have a centre
+        // strictly inside it
+        bad |= inf;
+        dmin = fminf(dmin, d);
         const float sig = d - 2e-7f;
         const int sp = (int)(inf & (kUnresolved - 1u));
         const float x0 = c.X[sp], x1 = c.X[sp + 1];
@@ -488,7 +490,7 @@ CS_HD bool fast_column(const Tab& c, int col, uint32_t* out_px) {
     const float lo = fminf(fminf(a0 - f0, a1 - f1), a2 - f2), hi = fmaxf(fmaxf(a0 - f0, a1 - f1), a2 - f2);
     *out_px = pack3((int)f0, (int)f1, (int)f2);
     // (NaN sums -- a degenerate interval divided by zero -- fail the comparison and go to the exact path)
-    return !(bad & kUnresolved) && lo >= E && hi <= 1.0f - E;
+    return !(bad & kUnresolved) && dmin >= 1e-6f && lo >= E && hi <= 1.0f - E;
 }
 
 // ------------------------------------------------------------------ interval classification
