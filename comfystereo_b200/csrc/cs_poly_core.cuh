@@ -510,7 +510,7 @@ CS_HD uint32_t classify_interval(const Tab& c, int k) {
     const float av = c.SX[k], bv = c.SX[k + 1];
     int cnt = 0, obest = -1, ohi1 = -1;
     float lo1 = -1.0f, lo2 = -1.0f, hib = -1.0f, hi1 = -1.0f, hi2 = -1.0f;     // closeness is >= 0: -1 is "none"
-    uint32_t spb = 0, first = 0;
+    uint32_t spb = 0;
     bool safe = true;
     float qmax = 0.0f;
     for (int j = k; j >= 0; --j) {
@@ -518,7 +518,6 @@ CS_HD uint32_t classify_interval(const Tab& c, int k) {
         if ((int)(er >> 16) <= k) break;            // nothing at or before j reaches past point k
         if ((int)(er & 0xFFFFu) > k) {
             const int sp = (int)c.SID[j];
-            if (cnt == 0) first = (uint32_t)sp;
             const float q0 = c.Q[pt_slot<SHARP>(sp)], q1 = c.Q[pt_slot<SHARP>(sp + 1)];
             const float x0 = c.SX[j], x1 = c.X[sp + 1];
             const float d = x1 - x0;
@@ -538,7 +537,7 @@ CS_HD uint32_t classify_interval(const Tab& c, int k) {
         }
     }
     const uint32_t own = (uint32_t)c.SID[k];
-    if (cnt == 1) return first;
+    if (cnt == 1) return (obest == 0) ? spb : (own | kUnresolved);   // (a NaN closeness -- zero-length segment -- is nobody's win)
     if (cnt < 1 || cnt > kMaxCand) return own | kUnresolved;
     // the leader at the left end must lead every other candidate by the margin at both ends
     const float margin = 1e-3f + 1e-4f * qmax;
