@@ -97,7 +97,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        if handle.cs_abi_version() != 3:
+        if handle.cs_abi_version() != 4:
             raise ImportError("libcomfystereo_b200.so: ABI version mismatch, rebuild it")
         _lib = handle
     return _lib

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 3
+#define CS_ABI_VERSION 4   /* 4: CS_FILL_GPU_WARP_MESH, cs_forward_warp_mesh, *_scratch_bytes; 3: progress callback, blur_flavor */
 
 #if defined(__GNUC__)
 #define CS_API __attribute__((visibility("default")))

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names  # the ctypes table binds exactly the header's surface
-    assert _lib.lib().cs_abi_version() == 3
+    assert _lib.lib().cs_abi_version() == 4
 
 
 def test_graft_entry_build():
