@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kSeg, 4) k_blur_blend(
     __shared__ float s_q[256];                   // k / 255.0f, the depth outputs' dequantisation (GS:365)
     const int tid = threadIdx.x;
     s_lut[tid] = lut.w[tid];
-    s_q[tid] = (float)tid / 255.0f;
+    s_q[tid] = kQ255[tid];
     if (tid == 0) s_lut[256] = 0.0f;
     const int frame = blockIdx.y;
     const float scale = frame_scale(st, frame, scale_mode, group, n);

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_hybrid_gapfill(const WarpArgs a, double
 __global__ void __launch_bounds__(256) k_hybrid_gapfill_fused(const WarpArgs a, double ws1, double ws2) {
     const int w = a.w, h = a.h, frame = blockIdx.y, eye = blockIdx.z;
     __shared__ float s_q255[256];
-    s_q255[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    s_q255[threadIdx.x] = kQ255[threadIdx.x];
     __syncthreads();
     const int64_t base_off = (int64_t)frame * h * w;
     const uint32_t* orig = a.image_u8 + base_off;

@@ -185,6 +185,43 @@ __device__ __forceinline__ int64_t fused_index(const WarpArgs& a, int eye, int f
     return ((int64_t)frame * ho + oy) * wo + ox;
 }
 
+// k / 255.0f for k = 0..255, the IEEE float32 quotients (the dequantisation of GS:365-378): kernels copy the table into
+// shared memory instead of dividing 256 times per CTA (the division was 4 % of k_warp_rows' instructions).
+static __device__ const float kQ255[256] = {
+    0x0.0p+0f, 0x1.0101020000000p-8f, 0x1.0101020000000p-7f, 0x1.8181820000000p-7f, 0x1.0101020000000p-6f, 0x1.4141420000000p-6f, 0x1.8181820000000p-6f, 0x1.c1c1c20000000p-6f,
+    0x1.0101020000000p-5f, 0x1.2121220000000p-5f, 0x1.4141420000000p-5f, 0x1.6161620000000p-5f, 0x1.8181820000000p-5f, 0x1.a1a1a20000000p-5f, 0x1.c1c1c20000000p-5f, 0x1.e1e1e20000000p-5f,
+    0x1.0101020000000p-4f, 0x1.1111120000000p-4f, 0x1.2121220000000p-4f, 0x1.3131320000000p-4f, 0x1.4141420000000p-4f, 0x1.5151520000000p-4f, 0x1.6161620000000p-4f, 0x1.7171720000000p-4f,
+    0x1.8181820000000p-4f, 0x1.9191920000000p-4f, 0x1.a1a1a20000000p-4f, 0x1.b1b1b20000000p-4f, 0x1.c1c1c20000000p-4f, 0x1.d1d1d20000000p-4f, 0x1.e1e1e20000000p-4f, 0x1.f1f1f20000000p-4f,
+    0x1.0101020000000p-3f, 0x1.09090a0000000p-3f, 0x1.1111120000000p-3f, 0x1.19191a0000000p-3f, 0x1.2121220000000p-3f, 0x1.29292a0000000p-3f, 0x1.3131320000000p-3f, 0x1.39393a0000000p-3f,
+    0x1.4141420000000p-3f, 0x1.49494a0000000p-3f, 0x1.5151520000000p-3f, 0x1.59595a0000000p-3f, 0x1.6161620000000p-3f, 0x1.69696a0000000p-3f, 0x1.7171720000000p-3f, 0x1.79797a0000000p-3f,
+    0x1.8181820000000p-3f, 0x1.89898a0000000p-3f, 0x1.9191920000000p-3f, 0x1.99999a0000000p-3f, 0x1.a1a1a20000000p-3f, 0x1.a9a9aa0000000p-3f, 0x1.b1b1b20000000p-3f, 0x1.b9b9ba0000000p-3f,
+    0x1.c1c1c20000000p-3f, 0x1.c9c9ca0000000p-3f, 0x1.d1d1d20000000p-3f, 0x1.d9d9da0000000p-3f, 0x1.e1e1e20000000p-3f, 0x1.e9e9ea0000000p-3f, 0x1.f1f1f20000000p-3f, 0x1.f9f9fa0000000p-3f,
+    0x1.0101020000000p-2f, 0x1.0505060000000p-2f, 0x1.09090a0000000p-2f, 0x1.0d0d0e0000000p-2f, 0x1.1111120000000p-2f, 0x1.1515160000000p-2f, 0x1.19191a0000000p-2f, 0x1.1d1d1e0000000p-2f,
+    0x1.2121220000000p-2f, 0x1.2525260000000p-2f, 0x1.29292a0000000p-2f, 0x1.2d2d2e0000000p-2f, 0x1.3131320000000p-2f, 0x1.3535360000000p-2f, 0x1.39393a0000000p-2f, 0x1.3d3d3e0000000p-2f,
+    0x1.4141420000000p-2f, 0x1.4545460000000p-2f, 0x1.49494a0000000p-2f, 0x1.4d4d4e0000000p-2f, 0x1.5151520000000p-2f, 0x1.5555560000000p-2f, 0x1.59595a0000000p-2f, 0x1.5d5d5e0000000p-2f,
+    0x1.6161620000000p-2f, 0x1.6565660000000p-2f, 0x1.69696a0000000p-2f, 0x1.6d6d6e0000000p-2f, 0x1.7171720000000p-2f, 0x1.7575760000000p-2f, 0x1.79797a0000000p-2f, 0x1.7d7d7e0000000p-2f,
+    0x1.8181820000000p-2f, 0x1.8585860000000p-2f, 0x1.89898a0000000p-2f, 0x1.8d8d8e0000000p-2f, 0x1.9191920000000p-2f, 0x1.9595960000000p-2f, 0x1.99999a0000000p-2f, 0x1.9d9d9e0000000p-2f,
+    0x1.a1a1a20000000p-2f, 0x1.a5a5a60000000p-2f, 0x1.a9a9aa0000000p-2f, 0x1.adadae0000000p-2f, 0x1.b1b1b20000000p-2f, 0x1.b5b5b60000000p-2f, 0x1.b9b9ba0000000p-2f, 0x1.bdbdbe0000000p-2f,
+    0x1.c1c1c20000000p-2f, 0x1.c5c5c60000000p-2f, 0x1.c9c9ca0000000p-2f, 0x1.cdcdce0000000p-2f, 0x1.d1d1d20000000p-2f, 0x1.d5d5d60000000p-2f, 0x1.d9d9da0000000p-2f, 0x1.ddddde0000000p-2f,
+    0x1.e1e1e20000000p-2f, 0x1.e5e5e60000000p-2f, 0x1.e9e9ea0000000p-2f, 0x1.ededee0000000p-2f, 0x1.f1f1f20000000p-2f, 0x1.f5f5f60000000p-2f, 0x1.f9f9fa0000000p-2f, 0x1.fdfdfe0000000p-2f,
+    0x1.0101020000000p-1f, 0x1.0303040000000p-1f, 0x1.0505060000000p-1f, 0x1.0707080000000p-1f, 0x1.09090a0000000p-1f, 0x1.0b0b0c0000000p-1f, 0x1.0d0d0e0000000p-1f, 0x1.0f0f100000000p-1f,
+    0x1.1111120000000p-1f, 0x1.1313140000000p-1f, 0x1.1515160000000p-1f, 0x1.1717180000000p-1f, 0x1.19191a0000000p-1f, 0x1.1b1b1c0000000p-1f, 0x1.1d1d1e0000000p-1f, 0x1.1f1f200000000p-1f,
+    0x1.2121220000000p-1f, 0x1.2323240000000p-1f, 0x1.2525260000000p-1f, 0x1.2727280000000p-1f, 0x1.29292a0000000p-1f, 0x1.2b2b2c0000000p-1f, 0x1.2d2d2e0000000p-1f, 0x1.2f2f300000000p-1f,
+    0x1.3131320000000p-1f, 0x1.3333340000000p-1f, 0x1.3535360000000p-1f, 0x1.3737380000000p-1f, 0x1.39393a0000000p-1f, 0x1.3b3b3c0000000p-1f, 0x1.3d3d3e0000000p-1f, 0x1.3f3f400000000p-1f,
+    0x1.4141420000000p-1f, 0x1.4343440000000p-1f, 0x1.4545460000000p-1f, 0x1.4747480000000p-1f, 0x1.49494a0000000p-1f, 0x1.4b4b4c0000000p-1f, 0x1.4d4d4e0000000p-1f, 0x1.4f4f500000000p-1f,
+    0x1.5151520000000p-1f, 0x1.5353540000000p-1f, 0x1.5555560000000p-1f, 0x1.5757580000000p-1f, 0x1.59595a0000000p-1f, 0x1.5b5b5c0000000p-1f, 0x1.5d5d5e0000000p-1f, 0x1.5f5f600000000p-1f,
+    0x1.6161620000000p-1f, 0x1.6363640000000p-1f, 0x1.6565660000000p-1f, 0x1.6767680000000p-1f, 0x1.69696a0000000p-1f, 0x1.6b6b6c0000000p-1f, 0x1.6d6d6e0000000p-1f, 0x1.6f6f700000000p-1f,
+    0x1.7171720000000p-1f, 0x1.7373740000000p-1f, 0x1.7575760000000p-1f, 0x1.7777780000000p-1f, 0x1.79797a0000000p-1f, 0x1.7b7b7c0000000p-1f, 0x1.7d7d7e0000000p-1f, 0x1.7f7f800000000p-1f,
+    0x1.8181820000000p-1f, 0x1.8383840000000p-1f, 0x1.8585860000000p-1f, 0x1.8787880000000p-1f, 0x1.89898a0000000p-1f, 0x1.8b8b8c0000000p-1f, 0x1.8d8d8e0000000p-1f, 0x1.8f8f900000000p-1f,
+    0x1.9191920000000p-1f, 0x1.9393940000000p-1f, 0x1.9595960000000p-1f, 0x1.9797980000000p-1f, 0x1.99999a0000000p-1f, 0x1.9b9b9c0000000p-1f, 0x1.9d9d9e0000000p-1f, 0x1.9f9fa00000000p-1f,
+    0x1.a1a1a20000000p-1f, 0x1.a3a3a40000000p-1f, 0x1.a5a5a60000000p-1f, 0x1.a7a7a80000000p-1f, 0x1.a9a9aa0000000p-1f, 0x1.ababac0000000p-1f, 0x1.adadae0000000p-1f, 0x1.afafb00000000p-1f,
+    0x1.b1b1b20000000p-1f, 0x1.b3b3b40000000p-1f, 0x1.b5b5b60000000p-1f, 0x1.b7b7b80000000p-1f, 0x1.b9b9ba0000000p-1f, 0x1.bbbbbc0000000p-1f, 0x1.bdbdbe0000000p-1f, 0x1.bfbfc00000000p-1f,
+    0x1.c1c1c20000000p-1f, 0x1.c3c3c40000000p-1f, 0x1.c5c5c60000000p-1f, 0x1.c7c7c80000000p-1f, 0x1.c9c9ca0000000p-1f, 0x1.cbcbcc0000000p-1f, 0x1.cdcdce0000000p-1f, 0x1.cfcfd00000000p-1f,
+    0x1.d1d1d20000000p-1f, 0x1.d3d3d40000000p-1f, 0x1.d5d5d60000000p-1f, 0x1.d7d7d80000000p-1f, 0x1.d9d9da0000000p-1f, 0x1.dbdbdc0000000p-1f, 0x1.ddddde0000000p-1f, 0x1.dfdfe00000000p-1f,
+    0x1.e1e1e20000000p-1f, 0x1.e3e3e40000000p-1f, 0x1.e5e5e60000000p-1f, 0x1.e7e7e80000000p-1f, 0x1.e9e9ea0000000p-1f, 0x1.ebebec0000000p-1f, 0x1.ededee0000000p-1f, 0x1.efeff00000000p-1f,
+    0x1.f1f1f20000000p-1f, 0x1.f3f3f40000000p-1f, 0x1.f5f5f60000000p-1f, 0x1.f7f7f80000000p-1f, 0x1.f9f9fa0000000p-1f, 0x1.fbfbfc0000000p-1f, 0x1.fdfdfe0000000p-1f, 0x1.0000000000000p+0f
+};
+
 void count_launch();
 int sm_count();           // SMs of the current device (148 on a B200), for grid sizing
 void release_graphs();   // cs_api.cu: drops the cached CUDA graphs of small repeated cs_stereo_batch calls

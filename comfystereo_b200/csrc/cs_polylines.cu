@@ -356,7 +356,7 @@ k_polylines(const WarpArgs a, const PolyGeom g, int* __restrict__ row_flags, int
     __shared__ int s_nslow, s_nhard, s_nflag;
     __shared__ float s_q255[256];     // k / 255.0f (GS:365-378), for the fused composed output
     __shared__ Tab s_tab;   // the exact path is a real function call and takes the tables by reference
-    for (int k = t; k < 256; k += NT) s_q255[k] = (float)k / 255.0f;
+    for (int k = t; k < 256; k += NT) s_q255[k] = kQ255[k];
     if (t == 0) {
         s_nslow = 0; s_nhard = 0; s_nflag = 0;
         s_tab.X = X; s_tab.SX = SX; s_tab.ER = ER; s_tab.SID = SID; s_tab.WSP = WSP; s_tab.Q = Q; s_tab.IMGP = IMGP;

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(rows_max_threads<FILL>()) k_warp_rows(const Wa
     // one finished pixel: the RGBX8 eye image, or (fused: side-by-side / top-bottom modes) its place in the composed
     // float32 tensor and the black-pixel mask (C1 + M1 + O1, SIG:1543-1552, GS:355-378) -- no k_compose pass then
     __shared__ float s_q255[256];
-    if (a.fused_stereo) for (int k = threadIdx.x; k < 256; k += blockDim.x) s_q255[k] = (float)k / 255.0f;   // visible after the first barrier
+    if (a.fused_stereo) for (int k = threadIdx.x; k < 256; k += blockDim.x) s_q255[k] = kQ255[k];   // visible after the first barrier
     const uint64_t pol = policy_evict_first();
     // (pixel by pixel: three 4-byte stores at a 12-byte stride per warp merge in L2; a warp-collective version that
     // shuffles the pixels into 128-bit stores measured 10 % slower)

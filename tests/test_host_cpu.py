@@ -206,3 +206,17 @@ def test_two_rank_gloo_sharding(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_k_over_255_table_is_the_ieee_quotient():
+    """cs_internal.cuh's literal table kQ255 (what the kernels dequantise with) must be float32(k) / float32(255) bit for bit."""
+    import re
+    import numpy as np
+    src = open(os.path.join(ROOT, "comfystereo_b200", "csrc", "cs_internal.cuh")).read()
+    body = src[src.index("kQ255[256] = {") + len("kQ255[256] = {"):]
+    body = body[:body.index("};")]
+    vals = [float.fromhex(t.rstrip("f")) for t in re.findall(r"0x[0-9a-fA-F.]+p[-+]?\d+f", body)]
+    assert len(vals) == 256
+    want = np.arange(256, dtype=np.float32) / np.float32(255)
+    assert np.array_equal(np.array(vals, np.float64).astype(np.float32), want)
+    assert np.array_equal(np.array(vals, np.float64), want.astype(np.float64))      # exactly representable as float32
