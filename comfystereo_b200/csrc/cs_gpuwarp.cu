@@ -92,8 +92,8 @@ __device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, c
     const int nwords = (w + 31) >> 5;
     float* ndv = smem_f;
     float* po = ndv + w;
-    float* dest = po + w;
-    float* src = dest + w;
+    float* src = po + w;        // (dest[x] = x + po[x] is recomputed where it is needed: 21 instead of 25 bytes per column
+                                //  lets five CTAs instead of four share an SM at 1080p)
     float* zb = src + w;
     int* win = reinterpret_cast<int*>(zb + w);
     uint32_t* fbits = reinterpret_cast<uint32_t*>(win + w + 16);   // filled (src >= 0) bitmap
@@ -152,7 +152,6 @@ __device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, c
             const float p = gw_offset(nm, dep[x], a.conv, a.expo, div_px, sep_px, &n);
             ndv[x] = n;
             po[x] = p;
-            dest[x] = (float)x + p;
         }
         __syncthreads();
 
@@ -167,7 +166,7 @@ __device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, c
         for (int x = threadIdx.x; x < w + 16; x += blockDim.x) M[x] = -1;
         __syncthreads();
         for (int i = threadIdx.x; i + 1 < w; i += blockDim.x) {
-            const float dl = dest[i], dr = dest[i + 1];
+            const float dl = (float)i + po[i], dr = (float)(i + 1) + po[i + 1];
             const float fl = floorf(fminf(dl, dr));
             const int cbc = (fl < -8.0f) ? -8 : ((fl > (float)(w + 7)) ? w + 7 : (int)fl);
             atomicMax(&M[cbc + 8], i);
@@ -205,7 +204,7 @@ __device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, c
                 }
                 if (i < 0) continue;
                 if (!((vm[i] >> k) & 1u)) continue;
-                const float dl = dest[i], dr = dest[i + 1];
+                const float dl = (float)i + po[i], dr = (float)(i + 1) + po[i + 1];
                 const bool connected = fabsf(po[i + 1] - po[i]) < 1.5f;
                 const float dm = fminf(dl, dr);
                 const long long c = (long long)floorf(dm) + k;
@@ -305,8 +304,8 @@ __device__ __forceinline__ void gpuwarp_row(const GpuWarpArgs& a, const int y, c
     for (int x = threadIdx.x; x < w; x += blockDim.x) mrow[x] = ((ubits[x >> 5] >> (x & 31)) & 1u) ? 1.0f : 0.0f;
 }
 
-template <int TPB>   // CTA size the kernel is compiled for (register budget): 256, or 512 for rows that leave room for two CTAs per SM
-__global__ void __launch_bounds__(TPB) k_gpuwarp(const GpuWarpArgs a) {
+template <int TPB>   // CTA size the kernel is compiled for (register budget): 256 (five CTAs per SM at 1080p), or 512 for rows that leave room for two CTAs per SM
+__global__ void __launch_bounds__(TPB, TPB == 256 ? 5 : 2) k_gpuwarp(const GpuWarpArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     gpuwarp_row(a, blockIdx.x, blockIdx.y, smem_f);
 }
@@ -622,7 +621,7 @@ cudaError_t launch_meshwarp(const GpuWarpArgs& a, cudaStream_t s) {
 
 cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
     const int nwords = (a.w + 31) >> 5;
-    size_t smem = (size_t)a.w * 24 + 64 + (size_t)nwords * 8 + (size_t)a.w + 16;
+    size_t smem = (size_t)a.w * 20 + 64 + (size_t)nwords * 8 + (size_t)a.w + 16;
     if (gw_row_bytes(a.w) > kRowSmemLimit) {
         if (!a.row_scratch || a.row_scratch_stride < gw_row_bytes(a.w)) return cudaErrorInvalidValue;
         prof_begin(K_GPUWARP, s);
@@ -631,7 +630,7 @@ cudaError_t launch_gpuwarp(const GpuWarpArgs& a, cudaStream_t s) {
         count_launch();
         return cudaGetLastError();
     }
-    // a row's shared memory (25 B per column) limits the CTAs per SM: keep ~32 warps resident by widening the CTA
+    // a row's shared memory (21 B per column) limits the CTAs per SM: keep ~32 warps resident by widening the CTA
     const bool wide = smem > 56 * 1024;
     if (smem > 48 * 1024) {
         if (wide) cudaFuncSetAttribute(k_gpuwarp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
