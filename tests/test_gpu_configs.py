@@ -464,3 +464,29 @@ def test_hot_path_is_capturable_in_a_callers_cuda_graph(fill, blur):
     torch.cuda.synchronize()
     for a, b in zip(outs, want2):
         assert torch.equal(a, b)
+
+
+def test_graph_cache_eviction_and_release():
+    """More distinct small jobs than the graph cache holds (16): entries are captured, evicted and destroyed while results
+    stay those of direct launches; cs_host_release drops whatever is cached and the next calls start over."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from comfystereo_b200 import engine
+    p = engine.make_params("naive", "left-right", 4.0, 0.0, 0.0, 0.5, 2.0, False, 9.0, 20.0, 2.0, 2)
+    jobs = []
+    for k in range(20):
+        h, w = 16 + 2 * k, 64 + 8 * k
+        img = torch.from_numpy(syn.make_image(1, h, w, seed=k)).cuda()
+        dep = torch.from_numpy(syn.make_depth(1, h, w, "scene", seed=k)).cuda()
+        want = [o.clone() for o in engine.stereo_batch_device(img.clone(), dep.clone(), p)]
+        out = engine.stereo_batch_device(img, dep, p)
+        jobs.append((img, dep, out, want))
+    for rounds in range(3):
+        for img, dep, out, want in jobs:
+            engine.stereo_batch_device(img, dep, p, out=out)
+        torch.cuda.synchronize()
+        for img, dep, out, want in jobs:
+            for a, b in zip(out, want):
+                assert torch.equal(a, b)
+        if rounds == 1:
+            engine.release()
